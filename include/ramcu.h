@@ -1,0 +1,164 @@
+/*
+ * ramcu.h -- the extern "C" ABI of the B200-native RAMExtend extension path.
+ *
+ * Host code stays C: the reference's main() (ram_extend.c:217-790) keeps calling
+ *     int extend_alignment(int direction, struct coreAlignment*, int ****score,
+ *                          struct sequenceLibrary*, char *master, int BANDWIDTH, int CAPPENALTY,
+ *                          int MINIMPROVEMENT, int L, int N, struct scoringSystem*, FILE*);
+ * (ram_extend.h:9-13). repeatafterme_b200/csrc/ramx_boundary.c provides a strong definition
+ * of that symbol which flattens the reference's structs and calls the entry points below;
+ * everything behind them is hand-written sm_100a CUDA (csrc/ramcu.cu). There is NO CPU fallback:
+ * every entry point fails (negative return, ramcu_last_error()) when no CUDA device is usable.
+ *
+ * Plain C types only; no torch / C++ types cross this boundary.
+ *
+ * Reference interface each item replaces:
+ *   ramcu_core_t         struct coreAlignment                  common.h:80-98
+ *   ramcu_scoring_t      struct scoringSystem                  score_system.h:7-17
+ *   ramcu_params_t       BANDWIDTH/CAPPENALTY/MINIMPROVEMENT/L args + WHEN_TO_STOP global
+ *                                                              ram_extend.h:9-13, ram_extend.c:61
+ *   ramcu_library_*      struct sequenceLibrary.sequence       sequence.h:36-46 (built by
+ *                        loadSequenceSubsetMinimal, sequence.c:505-923)
+ *   ramcu_extend         extend_alignment()                    ram_extend.c:859-1258
+ *                        (which drives compute_nw_row(), bnw_extend.c:750-1048)
+ *   ramcu_job_* / ramcu_batch_run
+ *                        the same call, split into prepare / enqueue / fetch so that many
+ *                        independent families (one RAMExtend process each in
+ *                        util/extend-stk.pl:365-371) share one context and run concurrently
+ *   ramcu_debug_rows     compute_nw_row() as called by the reference's unit tests
+ *                        (bnw_extend.c:1583,1600): forced consensus, band rows returned
+ */
+#ifndef RAMCU_H
+#define RAMCU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAMCU_ABI_VERSION 1
+#define RAMCU_NCODES 5            /* matrix columns: A,C,G,T,N (sequence.h:7-15; 99 -> 4)      */
+#define RAMCU_MAX_BANDWIDTH 511   /* 2*B+1 <= 1023 band cells                                  */
+
+/* error codes (all negative) */
+#define RAMCU_OK 0
+#define RAMCU_ERR_CUDA (-1)         /* CUDA runtime / no device                                */
+#define RAMCU_ERR_ARG (-2)          /* invalid argument                                        */
+#define RAMCU_ERR_UNSUPPORTED (-3)  /* outside what the kernels implement      */
+#define RAMCU_ERR_CAPACITY (-4)     /* family does not fit the device in one pass              */
+
+typedef struct ramcu_ctx ramcu_ctx;
+typedef struct ramcu_library ramcu_library;
+typedef struct ramcu_job ramcu_job;
+
+/* One MSA instance == one struct coreAlignment (common.h:80-98), flattened. Positions index the
+ * library's sequence[] array exactly as in the reference (0-based, closed). */
+typedef struct
+{
+  int64_t left_seq_pos;
+  int64_t right_seq_pos;
+  int64_t lower_seq_bound;
+  int64_t upper_seq_bound;
+  int8_t orient;             /* 1 = reverse strand */
+  int8_t left_extendable;
+  int8_t right_extendable;
+  int8_t pad_[5];
+} ramcu_core_t;
+
+/* matrix[consensus base 0..3][sequence code]: codes 0..3 = A,C,G,T, 4 = N (SYM_N and anything
+ * that is not 0..3). */
+typedef struct
+{
+  int32_t matrix[4][RAMCU_NCODES];
+  int32_t gapopen;
+  int32_t gapextn;
+} ramcu_scoring_t;
+
+typedef struct
+{
+  int32_t bandwidth;       /* MAXOFFSET/BANDWIDTH: band is 2*bandwidth+1 cells               */
+  int32_t cappenalty;
+  int32_t minimprovement;
+  int32_t L;               /* max extension length                                            */
+  int32_t when_to_stop;    /* WHEN_TO_STOP global (ram_extend.c:61,249)                        */
+  int32_t lanes_per_instance; /* 0 = auto; else force 1,2,4,8,16,32 (tuning/tests)            */
+  int32_t reserved[2];
+} ramcu_params_t;
+
+typedef struct
+{
+  int32_t extended_bp;     /* == return value of extend_alignment()                           */
+  int32_t rows_processed;  /* column-loop iterations executed                                 */
+  int32_t stop_row;        /* row_idx of the WHEN_TO_STOP break (for the VERBOSE>=3 line), -1 */
+  int32_t hit_limit;       /* 1 => reference prints "WARNING: Extended sequence ... limit"    */
+  int32_t max_score;       /* max_extension_score                                             */
+  int32_t n_extendable;    /* instances extendable in this direction                          */
+  float kernel_ms;         /* device time of the extension kernels (CUDA events), if measured  */
+  int32_t lanes_per_instance; /* configuration the launch used                                */
+} ramcu_result_t;
+
+const char *ramcu_last_error(void);
+int ramcu_abi_version(void);
+
+int ramcu_init(int device, ramcu_ctx **out);
+void ramcu_destroy(ramcu_ctx *ctx);
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = context's own. */
+int ramcu_set_stream(ramcu_ctx *ctx, void *cuda_stream);
+int ramcu_device_info(ramcu_ctx *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+
+/* Built-in scoring systems of score_system.c (getMatrix / getRepeatScoutMatrix). */
+int ramcu_scoring_by_name(const char *name, int rs_match, int rs_mismatch, int rs_gap,
+                          ramcu_scoring_t *out);
+
+/* Upload seqLib->sequence (1 byte per base: 0..3, 99) from HOST memory. The bytes are packed
+ * on the device to 2 bits/base + an N bitmask (the form the DP kernels read). */
+int ramcu_library_upload(ramcu_ctx *ctx, const uint8_t *seq_bytes, uint64_t length,
+                         ramcu_library **out);
+/* Same, but seq_bytes is already a DEVICE pointer (no host<->device copy). */
+int ramcu_library_from_device(ramcu_ctx *ctx, const uint8_t *d_seq_bytes, uint64_t length,
+                              ramcu_library **out);
+int ramcu_library_free(ramcu_ctx *ctx, ramcu_library *lib);
+
+/* One call == one call of the reference's extend_alignment() for `direction` (1 = right,
+ * 0 = left). Outputs (HOST memory):
+ *   master_out    : >= params->L bytes; master_out[r] = consensus base (0..3) chosen at row r,
+ *                   valid for r < res->rows_processed (caller maps r to master[] as in
+ *                   ram_extend.c:1092-1095)
+ *   ext_len_out   : n_cores ints; new right/leftExtensionLen, 0 = leave unchanged
+ *   score_add_out : n_cores ints; amount to add to coreAlignment.score
+ */
+int ramcu_extend(ramcu_ctx *ctx, ramcu_library *lib, int direction, int n_cores,
+                 const ramcu_core_t *cores, const ramcu_scoring_t *scoring,
+                 const ramcu_params_t *params, uint8_t *master_out, int32_t *ext_len_out,
+                 int32_t *score_add_out, ramcu_result_t *res);
+
+/* Split form. create: flatten + upload instance descriptors, allocate device state.
+ * run: enqueue the kernels on the context stream (asynchronous, inputs resident in HBM).
+ * fetch: wait + copy results to host. A job can be run repeatedly. */
+int ramcu_job_create(ramcu_ctx *ctx, ramcu_library *lib, int direction, int n_cores,
+                     const ramcu_core_t *cores, const ramcu_scoring_t *scoring,
+                     const ramcu_params_t *params, ramcu_job **out);
+int ramcu_job_run(ramcu_ctx *ctx, ramcu_job *job);
+int ramcu_job_fetch(ramcu_ctx *ctx, ramcu_job *job, uint8_t *master_out, int32_t *ext_len_out,
+                    int32_t *score_add_out, ramcu_result_t *res);
+int ramcu_job_free(ramcu_ctx *ctx, ramcu_job *job);
+
+/* Enqueue many independent jobs (families) so that they share the GPU concurrently. */
+int ramcu_batch_run(ramcu_ctx *ctx, int n_jobs, ramcu_job **jobs);
+
+/* Test-only second boundary (compute_nw_row, bnw_extend.h:52-58). Runs the extension kernel for
+ * `n_rows` rows with the consensus FORCED to forced_cons[r] (NULL = argmax as usual) and returns
+ *   rows_out : [n_rows][n_cores][2*B+1][2] committed band rows ([..][0]=sub, [..][1]=gap);
+ *              rows of instances not extendable in `direction` are left untouched
+ *   best_out : [n_rows][n_cores][4] per-candidate best row score (before clamp/cap)
+ *   sums_out : [n_rows][4] per-candidate column sums
+ */
+int ramcu_debug_rows(ramcu_ctx *ctx, ramcu_library *lib, int direction, int n_cores,
+                     const ramcu_core_t *cores, const ramcu_scoring_t *scoring,
+                     const ramcu_params_t *params, int n_rows, const uint8_t *forced_cons,
+                     int32_t *rows_out, int32_t *best_out, int32_t *sums_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

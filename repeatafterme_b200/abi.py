@@ -1,0 +1,258 @@
+"""ctypes mirror of include/ramcu.h (the product C-ABI) -- no torch types cross this boundary.
+
+The product path FAILS LOUDLY when ``csrc/libramcu.so`` is missing or no CUDA device is usable:
+there is no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libramcu.so")
+
+#: struct coreAlignment (reference common.h:80-98) flattened == ramcu_core_t
+CORE_DTYPE = np.dtype(
+    [
+        ("left_seq_pos", "<i8"),
+        ("right_seq_pos", "<i8"),
+        ("lower_seq_bound", "<i8"),
+        ("upper_seq_bound", "<i8"),
+        ("orient", "i1"),
+        ("left_extendable", "i1"),
+        ("right_extendable", "i1"),
+        ("pad_", "i1", (5,)),
+    ]
+)
+assert CORE_DTYPE.itemsize == 40
+
+NCODES = 5  # A,C,G,T,N
+
+#: every symbol include/ramcu.h declares
+ABI_SYMBOLS = (
+    "ramcu_last_error", "ramcu_abi_version", "ramcu_init", "ramcu_destroy", "ramcu_set_stream",
+    "ramcu_device_info", "ramcu_scoring_by_name", "ramcu_library_upload",
+    "ramcu_library_from_device", "ramcu_library_free", "ramcu_extend", "ramcu_job_create",
+    "ramcu_job_run", "ramcu_job_fetch", "ramcu_job_free", "ramcu_batch_run", "ramcu_debug_rows",
+)
+
+
+class Scoring(C.Structure):
+    """ramcu_scoring_t: matrix[cons 0..3][A,C,G,T,N] + gap penalties (score_system.h:7-17)."""
+
+    _fields_ = [("matrix", (C.c_int32 * NCODES) * 4), ("gapopen", C.c_int32), ("gapextn", C.c_int32)]
+
+    def as_array(self) -> np.ndarray:
+        return np.array([[self.matrix[a][b] for b in range(NCODES)] for a in range(4)], dtype=np.int32)
+
+    @staticmethod
+    def from_array(m, gapopen: int, gapextn: int) -> "Scoring":
+        s = Scoring()
+        for a in range(4):
+            for b in range(NCODES):
+                s.matrix[a][b] = int(m[a][b])
+        s.gapopen = int(gapopen)
+        s.gapextn = int(gapextn)
+        return s
+
+
+class Params(C.Structure):
+    """ramcu_params_t: the scalar arguments/globals of extend_alignment() (ram_extend.h:9-13)."""
+
+    _fields_ = [
+        ("bandwidth", C.c_int32),
+        ("cappenalty", C.c_int32),
+        ("minimprovement", C.c_int32),
+        ("L", C.c_int32),
+        ("when_to_stop", C.c_int32),
+        ("lanes_per_instance", C.c_int32),
+        ("reserved", C.c_int32 * 2),
+    ]
+
+
+class ExtendResult(C.Structure):
+    """ramcu_result_t."""
+
+    _fields_ = [
+        ("extended_bp", C.c_int32),
+        ("rows_processed", C.c_int32),
+        ("stop_row", C.c_int32),
+        ("hit_limit", C.c_int32),
+        ("max_score", C.c_int32),
+        ("n_extendable", C.c_int32),
+        ("kernel_ms", C.c_float),
+        ("lanes_per_instance", C.c_int32),
+    ]
+
+    def as_dict(self) -> dict:
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+def make_params(bandwidth=14, cappenalty=-90, minimprovement=27, L=10000, when_to_stop=100,
+                lanes_per_instance=0) -> Params:
+    """Defaults are those of the RAMExtend CLI (ram_extend.c:246-249, 301-344)."""
+    p = Params()
+    p.bandwidth, p.cappenalty, p.minimprovement, p.L, p.when_to_stop, p.lanes_per_instance = (
+        bandwidth, cappenalty, minimprovement, L, when_to_stop, lanes_per_instance)
+    return p
+
+
+class RamCuError(RuntimeError):
+    pass
+
+
+def load_ramcu(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise RamCuError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback for the product path."
+        )
+    lib = C.CDLL(path)
+    vp, i32, u64 = C.c_void_p, C.c_int32, C.c_uint64
+    P = C.POINTER
+    lib.ramcu_last_error.restype = C.c_char_p
+    lib.ramcu_last_error.argtypes = []
+    lib.ramcu_abi_version.restype = i32
+    lib.ramcu_init.argtypes = [i32, P(vp)]
+    lib.ramcu_destroy.argtypes = [vp]
+    lib.ramcu_destroy.restype = None
+    lib.ramcu_set_stream.argtypes = [vp, vp]
+    lib.ramcu_device_info.argtypes = [vp, P(i32), P(i32), P(i32)]
+    lib.ramcu_scoring_by_name.argtypes = [C.c_char_p, i32, i32, i32, P(Scoring)]
+    lib.ramcu_library_upload.argtypes = [vp, vp, u64, P(vp)]
+    lib.ramcu_library_from_device.argtypes = [vp, vp, u64, P(vp)]
+    lib.ramcu_library_free.argtypes = [vp, vp]
+    lib.ramcu_extend.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult)]
+    lib.ramcu_job_create.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), P(vp)]
+    lib.ramcu_job_run.argtypes = [vp, vp]
+    lib.ramcu_job_fetch.argtypes = [vp, vp, vp, vp, vp, P(ExtendResult)]
+    lib.ramcu_job_free.argtypes = [vp, vp]
+    lib.ramcu_batch_run.argtypes = [vp, i32, P(vp)]
+    lib.ramcu_debug_rows.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), i32, vp, vp, vp, vp]
+    for name in ABI_SYMBOLS:
+        if name not in ("ramcu_last_error", "ramcu_destroy"):
+            getattr(lib, name).restype = i32
+    return lib
+
+
+def scoring_by_name(lib: C.CDLL, name: str, rs=(1, -1, -5)) -> Scoring:
+    s = Scoring()
+    rc = lib.ramcu_scoring_by_name(name.encode(), rs[0], rs[1], rs[2], C.byref(s))
+    if rc:
+        raise RamCuError(lib.ramcu_last_error().decode())
+    return s
+
+
+class RamCu:
+    """Host-side mirror of the reference's extension interface, over the CUDA C-ABI.
+
+    ``extend(direction, ...)`` has the argument meaning of ``extend_alignment()``
+    (ram_extend.h:9-13): direction 1 = right, 0 = left; it returns the extended bp and the same
+    per-core side effects (extension length, score increment) as arrays.
+    """
+
+    def __init__(self, device: int = 0, path: str = LIB_PATH):
+        self.lib = load_ramcu(path)
+        self.ctx = C.c_void_p()
+        self._check(self.lib.ramcu_init(device, C.byref(self.ctx)))
+
+    def _check(self, rc: int):
+        if rc:
+            raise RamCuError(f"ramcu error {rc}: {self.lib.ramcu_last_error().decode()}")
+
+    def close(self):
+        if self.ctx:
+            self.lib.ramcu_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_info(self) -> dict:
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self.lib.ramcu_device_info(self.ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return {"sm_count": a.value, "cc": (b.value, c.value)}
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.ramcu_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)))
+
+    def scoring(self, name: str, rs=(1, -1, -5)) -> Scoring:
+        return scoring_by_name(self.lib, name, rs)
+
+    # -- library ---------------------------------------------------------------------------
+    def upload_library(self, seq: np.ndarray) -> C.c_void_p:
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        h = C.c_void_p()
+        self._check(self.lib.ramcu_library_upload(self.ctx, seq.ctypes.data, seq.size, C.byref(h)))
+        return h
+
+    def library_from_device(self, dev_ptr: int, length: int) -> C.c_void_p:
+        h = C.c_void_p()
+        self._check(self.lib.ramcu_library_from_device(self.ctx, C.c_void_p(dev_ptr), length, C.byref(h)))
+        return h
+
+    def free_library(self, h):
+        self._check(self.lib.ramcu_library_free(self.ctx, h))
+
+    # -- one extend_alignment() call ----------------------------------------------------------
+    def extend(self, lib_h, direction: int, cores: np.ndarray, scoring: Scoring, params: Params):
+        cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+        n = cores.size
+        master = np.zeros(max(params.L, 1), dtype=np.uint8)
+        ext_len = np.zeros(n, dtype=np.int32)
+        score_add = np.zeros(n, dtype=np.int32)
+        res = ExtendResult()
+        self._check(self.lib.ramcu_extend(self.ctx, lib_h, direction, n, cores.ctypes.data,
+                                          C.byref(scoring), C.byref(params), master.ctypes.data,
+                                          ext_len.ctypes.data, score_add.ctypes.data, C.byref(res)))
+        return res, master[: res.rows_processed].copy(), ext_len, score_add
+
+    # -- split form -------------------------------------------------------------------------
+    def job_create(self, lib_h, direction: int, cores: np.ndarray, scoring: Scoring, params: Params):
+        cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+        h = C.c_void_p()
+        self._check(self.lib.ramcu_job_create(self.ctx, lib_h, direction, cores.size, cores.ctypes.data,
+                                              C.byref(scoring), C.byref(params), C.byref(h)))
+        return h
+
+    def job_run(self, job):
+        self._check(self.lib.ramcu_job_run(self.ctx, job))
+
+    def batch_run(self, jobs):
+        arr = (C.c_void_p * len(jobs))(*[j.value for j in jobs])
+        self._check(self.lib.ramcu_batch_run(self.ctx, len(jobs), arr))
+
+    def job_fetch(self, job, n_cores: int, L: int):
+        master = np.zeros(max(L, 1), dtype=np.uint8)
+        ext_len = np.zeros(n_cores, dtype=np.int32)
+        score_add = np.zeros(n_cores, dtype=np.int32)
+        res = ExtendResult()
+        self._check(self.lib.ramcu_job_fetch(self.ctx, job, master.ctypes.data, ext_len.ctypes.data,
+                                             score_add.ctypes.data, C.byref(res)))
+        return res, master[: res.rows_processed].copy(), ext_len, score_add
+
+    def job_free(self, job):
+        self._check(self.lib.ramcu_job_free(self.ctx, job))
+
+    # -- test-only: compute_nw_row boundary -----------------------------------------------------
+    def debug_rows(self, lib_h, direction: int, cores: np.ndarray, scoring: Scoring, params: Params,
+                   n_rows: int, forced=None):
+        cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+        n, W = cores.size, 2 * params.bandwidth + 1
+        rows = np.zeros((n_rows, n, W, 2), dtype=np.int32)
+        best = np.zeros((n_rows, n, 4), dtype=np.int32)
+        sums = np.zeros((n_rows, 4), dtype=np.int32)
+        fptr = None
+        if forced is not None:
+            forced = np.ascontiguousarray(forced, dtype=np.uint8)
+            assert forced.size >= n_rows
+            fptr = forced.ctypes.data
+        self._check(self.lib.ramcu_debug_rows(self.ctx, lib_h, direction, n, cores.ctypes.data,
+                                              C.byref(scoring), C.byref(params), n_rows, fptr,
+                                              rows.ctypes.data, best.ctypes.data, sums.ctypes.data))
+        return rows, best, sums

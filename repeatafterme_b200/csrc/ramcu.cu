@@ -1,0 +1,721 @@
+// ramcu.cu -- extern "C" ABI (include/ramcu.h) over the sm_100a extension kernels.
+//
+// Host-side responsibilities (all cheap, O(N)): flatten the caller's cores into per-direction
+// instance descriptors (geometry of bnw_extend.c:778-788,824-837), pick a band tiling
+// (G lanes x C cells), size the grid so that every CTA of a family can be co-resident, launch,
+// and map results back (ram_extend.c:1234-1247). No DP arithmetic happens on the host and there
+// is no CPU fallback: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ramcu.h"
+#include "extend_kernel.cuh"
+#include "flatten.h"
+
+using namespace ramcu;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                         \
+  do                                                                                     \
+  {                                                                                      \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(RAMCU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// kernel registry: band tilings
+// ------------------------------------------------------------------------------------------
+typedef void (*extend_fn)(const FamDev *, const int *, int *);
+
+struct KernelCfg
+{
+  int B;    // bandwidth this instantiation is specialised for (-1 = any, runtime W)
+  int C;    // cells per lane
+  int G;    // lanes per instance
+  extend_fn fn;
+  int regs;            // filled at init
+  int max_cta_per_sm;  // at kThreads threads per CTA, filled at init
+};
+
+static const int kThreads = 128;
+
+#define RAMCU_CFG(B_, C_, G_) {B_, C_, G_, extend_kernel<C_, G_, 2 * B_ + 1>, 0, 0}
+#define RAMCU_GEN(C_, G_) {-1, C_, G_, extend_kernel<C_, G_, 0>, 0, 0}
+
+static KernelCfg g_cfgs[] = {
+  // RAMExtend default (ram_extend.c:247)
+  RAMCU_CFG(14, 29, 1), RAMCU_CFG(14, 15, 2), RAMCU_CFG(14, 8, 4), RAMCU_CFG(14, 4, 8),
+  RAMCU_CFG(20, 41, 1), RAMCU_CFG(20, 21, 2), RAMCU_CFG(20, 11, 4),
+  // util/extend-stk.pl:365
+  RAMCU_CFG(40, 81, 1), RAMCU_CFG(40, 41, 2), RAMCU_CFG(40, 21, 4), RAMCU_CFG(40, 11, 8),
+  RAMCU_CFG(60, 31, 4), RAMCU_CFG(60, 16, 8), RAMCU_CFG(60, 8, 16),
+  RAMCU_CFG(80, 41, 4), RAMCU_CFG(80, 21, 8),
+  RAMCU_CFG(100, 51, 4), RAMCU_CFG(100, 26, 8), RAMCU_CFG(100, 13, 16),
+  // any other bandwidth: runtime band width, fully predicated cells
+  RAMCU_GEN(4, 4), RAMCU_GEN(8, 4), RAMCU_GEN(16, 4), RAMCU_GEN(32, 4),
+  RAMCU_GEN(16, 16), RAMCU_GEN(32, 16), RAMCU_GEN(16, 32), RAMCU_GEN(32, 32),
+};
+static const int g_ncfg = (int) (sizeof(g_cfgs) / sizeof(g_cfgs[0]));
+
+// ------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------
+struct ramcu_ctx
+{
+  int device;
+  int sm_count, cc_major, cc_minor;
+  cudaStream_t own_stream, stream;
+  cudaEvent_t ev0, ev1;
+  int *d_ticket;
+};
+
+struct ramcu_library
+{
+  uint64_t length;
+  uint32_t *d_lib2;  // padded by 2 words at both ends; pointer is to base 0
+  uint32_t *d_libn;
+  void *alloc2, *allocn;
+};
+
+struct ramcu_job
+{
+  ramcu_library *lib;
+  int direction, n_cores, n_ext;
+  ramcu_scoring_t sc;
+  ramcu_params_t pr;
+  const KernelCfg *cfg;
+  int n_ctas;
+  std::vector<int> orig;      // ext index -> core index
+  FamDev fam;                 // host copy (device pointers inside)
+  // device
+  InstDev *d_inst;
+  unsigned char *d_master;
+  int *d_thigh, *d_tpos, *d_result;
+  unsigned long long *d_slots;
+  FamDev *d_fam;      // single-family launch
+  int *d_cta_fam;     // zeros, n_ctas
+  unsigned char *d_forced;
+  int *d_dbg_rows, *d_dbg_best, *d_dbg_sums;
+  bool ran, timed;
+};
+
+// ------------------------------------------------------------------------------------------
+// basic entry points
+// ------------------------------------------------------------------------------------------
+extern "C" const char *ramcu_last_error(void) { return g_err; }
+extern "C" int ramcu_abi_version(void) { return RAMCU_ABI_VERSION; }
+
+extern "C" int ramcu_init(int device, ramcu_ctx **out)
+{
+  if (!out)
+    return fail(RAMCU_ERR_ARG, "ramcu_init: out == NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(RAMCU_ERR_CUDA, "ramcu_init: no CUDA device (%s); there is no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n)
+    return fail(RAMCU_ERR_ARG, "ramcu_init: device %d out of range (0..%d)", device, n - 1);
+  CK(cudaSetDevice(device));
+  ramcu_ctx *c = new ramcu_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  CK(cudaMalloc(&c->d_ticket, sizeof(int)));
+  for (int i = 0; i < g_ncfg; ++i)
+  {
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, (const void *) g_cfgs[i].fn);
+    if (e != cudaSuccess)
+    {
+      delete c;
+      return fail(RAMCU_ERR_CUDA,
+                  "ramcu_init: kernel image not loadable on this device (built for sm_100a): %s",
+                  cudaGetErrorString(e));
+    }
+    g_cfgs[i].regs = fa.numRegs;
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *) g_cfgs[i].fn, kThreads, 0));
+    g_cfgs[i].max_cta_per_sm = nb;
+  }
+  *out = c;
+  return RAMCU_OK;
+}
+
+extern "C" void ramcu_destroy(ramcu_ctx *c)
+{
+  if (!c)
+    return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_ticket);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+extern "C" int ramcu_set_stream(ramcu_ctx *c, void *s)
+{
+  if (!c)
+    return fail(RAMCU_ERR_ARG, "ramcu_set_stream: ctx == NULL");
+  c->stream = s ? (cudaStream_t) s : c->own_stream;
+  return RAMCU_OK;
+}
+
+extern "C" int ramcu_device_info(ramcu_ctx *c, int32_t *sm, int32_t *maj, int32_t *min)
+{
+  if (!c)
+    return fail(RAMCU_ERR_ARG, "ramcu_device_info: ctx == NULL");
+  if (sm) *sm = c->sm_count;
+  if (maj) *maj = c->cc_major;
+  if (min) *min = c->cc_minor;
+  return RAMCU_OK;
+}
+
+// Built-in tables: facts of score_system.c:207-376 (matrix[consensus][sequence]); N scores -1
+// (score_system.c:384-395); "repeatscout" (score_system.c:91-172) has gapopen 0, gapextn = gap
+// and every non-identical pair (N included) = mismatch.
+extern "C" int ramcu_scoring_by_name(const char *name, int rs_match, int rs_mismatch, int rs_gap,
+                                     ramcu_scoring_t *out)
+{
+  static const struct
+  {
+    const char *name;
+    int go, ge;
+    int m[4][4];
+  } T[] = {
+    {"14p43g", -33, -7, {{9, -18, -10, -21}, {-18, 11, -18, -7}, {-7, -18, 11, -18}, {-21, -10, -18, 9}}},
+    {"18p43g", -30, -6, {{9, -15, -8, -18}, {-16, 10, -16, -5}, {-5, -16, 10, -16}, {-18, -8, -15, 9}}},
+    {"20p43g", -28, -5, {{9, -15, -8, -17}, {-15, 10, -15, -4}, {-4, -15, 10, -15}, {-17, -8, -15, 9}}},
+    {"25p43g", -25, -5, {{8, -13, -6, -15}, {-13, 9, -13, -2}, {-2, -13, 9, -13}, {-15, -6, -13, 8}}},
+  };
+  if (!name || !out)
+    return fail(RAMCU_ERR_ARG, "ramcu_scoring_by_name: NULL argument");
+  memset(out, 0, sizeof(*out));
+  if (strcmp(name, "repeatscout") == 0)
+  {
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < RAMCU_NCODES; ++b)
+        out->matrix[a][b] = (a == b) ? rs_match : rs_mismatch;
+    out->gapopen = 0;
+    out->gapextn = rs_gap;
+    return RAMCU_OK;
+  }
+  for (size_t i = 0; i < sizeof(T) / sizeof(T[0]); ++i)
+    if (strcmp(name, T[i].name) == 0)
+    {
+      for (int a = 0; a < 4; ++a)
+      {
+        for (int b = 0; b < 4; ++b)
+          out->matrix[a][b] = T[i].m[a][b];
+        out->matrix[a][4] = -1;
+      }
+      out->gapopen = T[i].go;
+      out->gapextn = T[i].ge;
+      return RAMCU_OK;
+    }
+  return fail(RAMCU_ERR_ARG, "Matrix name not found: %s", name);
+}
+
+// ------------------------------------------------------------------------------------------
+// library
+// ------------------------------------------------------------------------------------------
+static int library_pack(ramcu_ctx *c, const uint8_t *d_bytes, uint64_t length, ramcu_library **out)
+{
+  ramcu_library *lib = new ramcu_library();
+  lib->length = length;
+  const uint64_t n_chunks = (length + 31) / 32;  // 32 bases per chunk
+  const size_t pad = 4;                           // words of slack on both sides
+  CK(cudaMalloc(&lib->alloc2, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t)));
+  CK(cudaMalloc(&lib->allocn, (n_chunks + 2 * pad) * sizeof(uint32_t)));
+  CK(cudaMemsetAsync(lib->alloc2, 0, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(lib->allocn, 0xff, (n_chunks + 2 * pad) * sizeof(uint32_t), c->stream));
+  lib->d_lib2 = (uint32_t *) lib->alloc2 + pad;
+  lib->d_libn = (uint32_t *) lib->allocn + pad;
+  if (n_chunks > 0)
+  {
+    const unsigned long long want = (n_chunks + 255) / 256;
+    const int grid = (int) std::min<unsigned long long>(want, (unsigned long long) c->sm_count * 16);
+    pack_library_kernel<<<grid, 256, 0, c->stream>>>(d_bytes, length, lib->d_lib2, lib->d_libn,
+                                                     n_chunks);
+    CK(cudaGetLastError());
+  }
+  *out = lib;
+  return RAMCU_OK;
+}
+
+extern "C" int ramcu_library_upload(ramcu_ctx *c, const uint8_t *seq, uint64_t length,
+                                    ramcu_library **out)
+{
+  if (!c || !out || (!seq && length))
+    return fail(RAMCU_ERR_ARG, "ramcu_library_upload: NULL argument");
+  CK(cudaSetDevice(c->device));
+  uint8_t *d_bytes = nullptr;
+  CK(cudaMalloc(&d_bytes, length ? length : 1));
+  CK(cudaMemcpyAsync(d_bytes, seq, length, cudaMemcpyHostToDevice, c->stream));
+  int rc = library_pack(c, d_bytes, length, out);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_bytes);
+  return rc;
+}
+
+extern "C" int ramcu_library_from_device(ramcu_ctx *c, const uint8_t *d_seq, uint64_t length,
+                                         ramcu_library **out)
+{
+  if (!c || !out || (!d_seq && length))
+    return fail(RAMCU_ERR_ARG, "ramcu_library_from_device: NULL argument");
+  CK(cudaSetDevice(c->device));
+  return library_pack(c, d_seq, length, out);
+}
+
+extern "C" int ramcu_library_free(ramcu_ctx *c, ramcu_library *lib)
+{
+  if (!lib)
+    return RAMCU_OK;
+  if (c)
+  {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+  }
+  cudaFree(lib->alloc2);
+  cudaFree(lib->allocn);
+  delete lib;
+  return RAMCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// jobs
+// ------------------------------------------------------------------------------------------
+static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force_G,
+                                 long long other_threads)
+{
+  const int W = 2 * B + 1;
+  std::vector<const KernelCfg *> cand;
+  for (int i = 0; i < g_ncfg; ++i)
+    if (g_cfgs[i].B == B)
+      cand.push_back(&g_cfgs[i]);
+  if (cand.empty())
+    for (int i = 0; i < g_ncfg; ++i)
+      if (g_cfgs[i].B < 0 && g_cfgs[i].C * g_cfgs[i].G >= W &&
+          (g_cfgs[i].G - 1) * g_cfgs[i].C < W)
+        cand.push_back(&g_cfgs[i]);
+  if (cand.empty())
+    for (int i = 0; i < g_ncfg; ++i)  // narrow bands: last lanes may be entirely padding
+      if (g_cfgs[i].B < 0 && g_cfgs[i].C * g_cfgs[i].G >= W)
+      {
+        cand.push_back(&g_cfgs[i]);
+        break;
+      }
+  if (cand.empty())
+    return nullptr;
+  std::sort(cand.begin(), cand.end(),
+            [](const KernelCfg *a, const KernelCfg *b) { return a->G < b->G; });
+  auto fits = [&](const KernelCfg *k) {
+    const long long ctas = ((long long) n_ext * k->G + kThreads - 1) / kThreads;
+    return ctas <= (long long) k->max_cta_per_sm * c->sm_count;
+  };
+  if (force_G > 0)
+  {
+    for (const KernelCfg *k : cand)
+      if (k->G == force_G && fits(k))
+        return k;
+    return nullptr;
+  }
+  // Fewest lanes per instance (least cross-lane overhead) that still gives the GPU enough
+  // threads; families that fill the device on their own keep G small.
+  const long long target = (long long) c->sm_count * 256;
+  const KernelCfg *best = nullptr;
+  for (const KernelCfg *k : cand)
+  {
+    if (!fits(k))
+      continue;
+    best = k;
+    if ((long long) n_ext * k->G + other_threads >= target)
+      break;
+  }
+  return best;
+}
+
+static void free_job_device(ramcu_job *j)
+{
+  cudaFree(j->d_inst);
+  cudaFree(j->d_master);
+  cudaFree(j->d_thigh);
+  cudaFree(j->d_tpos);
+  cudaFree(j->d_result);
+  cudaFree(j->d_slots);
+  cudaFree(j->d_fam);
+  cudaFree(j->d_cta_fam);
+  cudaFree(j->d_forced);
+  cudaFree(j->d_dbg_rows);
+  cudaFree(j->d_dbg_best);
+  cudaFree(j->d_dbg_sums);
+}
+
+static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
+                           const ramcu_core_t *cores, const ramcu_scoring_t *sc,
+                           const ramcu_params_t *pr, int dbg_rows, const uint8_t *forced,
+                           ramcu_job **out)
+{
+  if (!c || !lib || !sc || !pr || !out || (n_cores > 0 && !cores))
+    return fail(RAMCU_ERR_ARG, "ramcu_job_create: NULL argument");
+  if (n_cores < 0 || pr->L < 0)
+    return fail(RAMCU_ERR_ARG, "ramcu_job_create: negative size");
+  if (pr->bandwidth < 0 || pr->bandwidth > RAMCU_MAX_BANDWIDTH)
+    return fail(RAMCU_ERR_UNSUPPORTED, "bandwidth %d outside 0..%d", pr->bandwidth,
+                RAMCU_MAX_BANDWIDTH);
+  if (pr->L > (1 << 24))
+    return fail(RAMCU_ERR_UNSUPPORTED, "L %d larger than %d", pr->L, 1 << 24);
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < RAMCU_NCODES; ++b)
+      if (abs(sc->matrix[a][b]) > 100000)
+        return fail(RAMCU_ERR_UNSUPPORTED, "matrix value %d too large", sc->matrix[a][b]);
+  if (abs(sc->gapopen) > 100000 || abs(sc->gapextn) > 100000)
+    return fail(RAMCU_ERR_UNSUPPORTED, "gap penalties too large");
+  CK(cudaSetDevice(c->device));
+
+  ramcu_job *j = new ramcu_job();
+  j->lib = lib;
+  j->direction = direction ? 1 : 0;
+  j->n_cores = n_cores;
+  j->sc = *sc;
+  j->pr = *pr;
+  j->ran = false;
+  j->timed = false;
+
+  const int B = pr->bandwidth;
+  std::vector<InstDev> inst;
+  flatten_cores(j->direction, n_cores, cores, lib->length, inst);
+  j->n_ext = (int) inst.size();
+  j->orig.resize(inst.size());
+  for (size_t i = 0; i < inst.size(); ++i)
+    j->orig[i] = inst[i].orig;
+
+  j->cfg = nullptr;
+  j->n_ctas = 0;
+  if (j->n_ext > 0 && pr->L > 0)
+  {
+    j->cfg = pick_cfg(c, B, j->n_ext, pr->lanes_per_instance, 0);
+    if (!j->cfg)
+    {
+      delete j;
+      return fail(RAMCU_ERR_CAPACITY,
+                  "no band tiling for bandwidth %d with %d instances fits this device "
+                  "(lanes_per_instance=%d)", B, (int) inst.size(), pr->lanes_per_instance);
+    }
+    j->n_ctas = (int) (((long long) j->n_ext * j->cfg->G + kThreads - 1) / kThreads);
+
+    const int W = 2 * B + 1;
+    CK(cudaMalloc(&j->d_inst, inst.size() * sizeof(InstDev)));
+    CK(cudaMemcpyAsync(j->d_inst, inst.data(), inst.size() * sizeof(InstDev),
+                       cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMalloc(&j->d_master, std::max(pr->L, 1)));
+    CK(cudaMalloc(&j->d_thigh, inst.size() * sizeof(int)));
+    CK(cudaMalloc(&j->d_tpos, inst.size() * sizeof(int)));
+    CK(cudaMalloc(&j->d_result, 8 * sizeof(int)));
+    CK(cudaMalloc(&j->d_slots, (size_t) 2 * j->n_ctas * 4 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&j->d_fam, sizeof(FamDev)));
+    CK(cudaMalloc(&j->d_cta_fam, j->n_ctas * sizeof(int)));
+    CK(cudaMemsetAsync(j->d_cta_fam, 0, j->n_ctas * sizeof(int), c->stream));
+    if (dbg_rows > 0)
+    {
+      CK(cudaMalloc(&j->d_dbg_rows, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int)));
+      CK(cudaMalloc(&j->d_dbg_best, (size_t) dbg_rows * j->n_ext * 4 * sizeof(int)));
+      CK(cudaMalloc(&j->d_dbg_sums, (size_t) dbg_rows * 4 * sizeof(int)));
+      CK(cudaMemsetAsync(j->d_dbg_rows, 0, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int), c->stream));
+      if (forced)
+      {
+        CK(cudaMalloc(&j->d_forced, dbg_rows));
+        CK(cudaMemcpyAsync(j->d_forced, forced, dbg_rows, cudaMemcpyHostToDevice, c->stream));
+      }
+    }
+    FamDev &f = j->fam;
+    fill_family(f, sc, pr, j->n_ext, j->n_ctas);
+    f.lib2 = lib->d_lib2;
+    f.libn = lib->d_libn;
+    f.inst = j->d_inst;
+    f.master = j->d_master;
+    f.thigh = j->d_thigh;
+    f.tpos = j->d_tpos;
+    f.result = j->d_result;
+    f.slots = j->d_slots;
+    f.forced = j->d_forced;
+    f.dbg_rows = j->d_dbg_rows;
+    f.dbg_best = j->d_dbg_best;
+    f.dbg_sums = j->d_dbg_sums;
+    CK(cudaMemcpyAsync(j->d_fam, &f, sizeof(f), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // `inst` and `f` are stack/heap temporaries
+  }
+  *out = j;
+  return RAMCU_OK;
+}
+
+extern "C" int ramcu_job_create(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
+                                const ramcu_core_t *cores, const ramcu_scoring_t *sc,
+                                const ramcu_params_t *pr, ramcu_job **out)
+{
+  return job_create_impl(c, lib, direction, n_cores, cores, sc, pr, 0, nullptr, out);
+}
+
+static int launch_single(ramcu_ctx *c, ramcu_job *j)
+{
+  CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(int), c->stream));
+  CK(cudaMemsetAsync(j->d_slots, 0, (size_t) 2 * j->n_ctas * 4 * sizeof(unsigned long long), c->stream));
+  j->cfg->fn<<<j->n_ctas, kThreads, 0, c->stream>>>(j->d_fam, j->d_cta_fam, c->d_ticket);
+  CK(cudaGetLastError());
+  return RAMCU_OK;
+}
+
+extern "C" int ramcu_job_run(ramcu_ctx *c, ramcu_job *j)
+{
+  if (!c || !j)
+    return fail(RAMCU_ERR_ARG, "ramcu_job_run: NULL argument");
+  CK(cudaSetDevice(c->device));
+  j->ran = true;
+  j->timed = false;
+  if (j->n_ctas == 0)
+    return RAMCU_OK;
+  CK(cudaEventRecord(c->ev0, c->stream));
+  int rc = launch_single(c, j);
+  if (rc)
+    return rc;
+  CK(cudaEventRecord(c->ev1, c->stream));
+  j->timed = true;
+  return RAMCU_OK;
+}
+
+extern "C" int ramcu_job_fetch(ramcu_ctx *c, ramcu_job *j, uint8_t *master_out, int32_t *ext_len_out,
+                               int32_t *score_add_out, ramcu_result_t *res)
+{
+  if (!c || !j || !res)
+    return fail(RAMCU_ERR_ARG, "ramcu_job_fetch: NULL argument");
+  if (!j->ran)
+    return fail(RAMCU_ERR_ARG, "ramcu_job_fetch: job was never run");
+  CK(cudaSetDevice(c->device));
+  memset(res, 0, sizeof(*res));
+  res->n_extendable = j->n_ext;
+  map_results(j->n_cores, std::vector<int>(), nullptr, nullptr, ext_len_out, score_add_out);
+  if (j->n_ctas == 0)
+  {
+    // No instance to extend: every column sums to 0, so 'A' is chosen and the loop stops after
+    // WHEN_TO_STOP rows without ever setting a maximum (ram_extend.c:973-974,1194,1216).
+    const int L = j->pr.L, stop = j->pr.when_to_stop;
+    int rows = 0, stop_row = -1, max_row = -1;
+    for (int r = 0; r < L; ++r)
+    {
+      rows = r + 1;
+      if (0 >= 0 + abs(max_row - r) * j->pr.minimprovement)
+        max_row = r;
+      if (r - max_row >= stop)
+      {
+        stop_row = r;
+        break;
+      }
+    }
+    if (master_out)
+      memset(master_out, 0, rows);
+    res->extended_bp = max_row + 1;
+    res->rows_processed = rows;
+    res->stop_row = stop_row;
+    res->hit_limit = (stop_row >= 0 && stop_row == L - 1) ? 1 : 0;
+    return RAMCU_OK;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  int r4[8];
+  CK(cudaMemcpy(r4, j->d_result, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  res->extended_bp = r4[0] + 1;
+  res->rows_processed = r4[1];
+  res->stop_row = r4[2];
+  res->max_score = r4[3];
+  res->hit_limit = (r4[2] >= 0 && r4[2] == j->pr.L - 1) ? 1 : 0;
+  res->lanes_per_instance = j->cfg->G;
+  if (j->timed)
+  {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+      res->kernel_ms = ms;
+  }
+  if (master_out && r4[1] > 0)
+    CK(cudaMemcpy(master_out, j->d_master, r4[1], cudaMemcpyDeviceToHost));
+  if (ext_len_out || score_add_out)
+  {
+    std::vector<int> th(j->n_ext), tp(j->n_ext);
+    CK(cudaMemcpy(th.data(), j->d_thigh, j->n_ext * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tp.data(), j->d_tpos, j->n_ext * sizeof(int), cudaMemcpyDeviceToHost));
+    map_results(j->n_cores, j->orig, th.data(), tp.data(), ext_len_out, score_add_out);
+  }
+  return RAMCU_OK;
+}
+
+extern "C" int ramcu_job_free(ramcu_ctx *c, ramcu_job *j)
+{
+  if (!j)
+    return RAMCU_OK;
+  if (c)
+  {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+  }
+  free_job_device(j);
+  delete j;
+  return RAMCU_OK;
+}
+
+extern "C" int ramcu_extend(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
+                            const ramcu_core_t *cores, const ramcu_scoring_t *sc,
+                            const ramcu_params_t *pr, uint8_t *master_out, int32_t *ext_len_out,
+                            int32_t *score_add_out, ramcu_result_t *res)
+{
+  ramcu_job *j = nullptr;
+  int rc = ramcu_job_create(c, lib, direction, n_cores, cores, sc, pr, &j);
+  if (rc)
+    return rc;
+  rc = ramcu_job_run(c, j);
+  if (!rc)
+    rc = ramcu_job_fetch(c, j, master_out, ext_len_out, score_add_out, res);
+  ramcu_job_free(c, j);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// batches: many independent families sharing the device
+// ------------------------------------------------------------------------------------------
+extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
+{
+  if (!c || (n_jobs > 0 && !jobs))
+    return fail(RAMCU_ERR_ARG, "ramcu_batch_run: NULL argument");
+  CK(cudaSetDevice(c->device));
+  // group by kernel instantiation; one launch per group, families ordered by decreasing work
+  std::vector<int> order;
+  for (int i = 0; i < n_jobs; ++i)
+  {
+    if (!jobs[i])
+      return fail(RAMCU_ERR_ARG, "ramcu_batch_run: jobs[%d] == NULL", i);
+    jobs[i]->ran = true;
+    jobs[i]->timed = false;
+    if (jobs[i]->n_ctas > 0)
+      order.push_back(i);
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    if (jobs[a]->cfg != jobs[b]->cfg)
+      return jobs[a]->cfg < jobs[b]->cfg;
+    const long long wa = (long long) jobs[a]->n_ext * jobs[a]->pr.L;
+    const long long wb = (long long) jobs[b]->n_ext * jobs[b]->pr.L;
+    return wa > wb;
+  });
+  CK(cudaEventRecord(c->ev0, c->stream));
+  size_t p = 0;
+  while (p < order.size())
+  {
+    size_t q = p;
+    const KernelCfg *cfg = jobs[order[p]]->cfg;
+    std::vector<FamDev> fams;
+    std::vector<int> cta_fam;
+    while (q < order.size() && jobs[order[q]]->cfg == cfg)
+    {
+      ramcu_job *j = jobs[order[q]];
+      FamDev f = j->fam;
+      f.cta0 = (int) cta_fam.size();
+      for (int k = 0; k < j->n_ctas; ++k)
+        cta_fam.push_back((int) fams.size());
+      fams.push_back(f);
+      CK(cudaMemsetAsync(j->d_slots, 0, (size_t) 2 * j->n_ctas * 4 * sizeof(unsigned long long),
+                         c->stream));
+      ++q;
+    }
+    FamDev *d_fams = nullptr;
+    int *d_map = nullptr;
+    CK(cudaMallocAsync(&d_fams, fams.size() * sizeof(FamDev), c->stream));
+    CK(cudaMallocAsync(&d_map, cta_fam.size() * sizeof(int), c->stream));
+    CK(cudaMemcpyAsync(d_fams, fams.data(), fams.size() * sizeof(FamDev), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_map, cta_fam.data(), cta_fam.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(int), c->stream));
+    // pageable sources: the copies above have completed on return, so the vectors may go away
+    cfg->fn<<<(int) cta_fam.size(), kThreads, 0, c->stream>>>(d_fams, d_map, c->d_ticket);
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(d_fams, c->stream));
+    CK(cudaFreeAsync(d_map, c->stream));
+    p = q;
+  }
+  CK(cudaEventRecord(c->ev1, c->stream));
+  for (int i : order)
+    jobs[i]->timed = true;
+  return RAMCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// test-only: forced-consensus rows (compute_nw_row boundary)
+// ------------------------------------------------------------------------------------------
+extern "C" int ramcu_debug_rows(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
+                                const ramcu_core_t *cores, const ramcu_scoring_t *sc,
+                                const ramcu_params_t *pr, int n_rows, const uint8_t *forced,
+                                int32_t *rows_out, int32_t *best_out, int32_t *sums_out)
+{
+  if (n_rows <= 0)
+    return fail(RAMCU_ERR_ARG, "ramcu_debug_rows: n_rows <= 0");
+  ramcu_params_t p = *pr;
+  p.L = n_rows;
+  p.when_to_stop = 1 << 30;
+  ramcu_job *j = nullptr;
+  int rc = job_create_impl(c, lib, direction, n_cores, cores, sc, &p, n_rows, forced, &j);
+  if (rc)
+    return rc;
+  const int W = 2 * p.bandwidth + 1;
+  if (j->n_ctas > 0)
+  {
+    rc = ramcu_job_run(c, j);
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess)
+      rc = fail(RAMCU_ERR_CUDA, "ramcu_debug_rows: kernel failed: %s",
+                cudaGetErrorString(cudaGetLastError()));
+    if (!rc)
+    {
+      std::vector<int> rows((size_t) n_rows * j->n_ext * W * 2), best((size_t) n_rows * j->n_ext * 4);
+      cudaMemcpy(rows.data(), j->d_dbg_rows, rows.size() * sizeof(int), cudaMemcpyDeviceToHost);
+      cudaMemcpy(best.data(), j->d_dbg_best, best.size() * sizeof(int), cudaMemcpyDeviceToHost);
+      if (sums_out)
+        cudaMemcpy(sums_out, j->d_dbg_sums, (size_t) n_rows * 4 * sizeof(int), cudaMemcpyDeviceToHost);
+      for (int r = 0; r < n_rows; ++r)
+        for (int e = 0; e < j->n_ext; ++e)
+        {
+          const int i = j->orig[e];
+          if (rows_out)
+            memcpy(rows_out + ((size_t) r * n_cores + i) * W * 2,
+                   rows.data() + ((size_t) r * j->n_ext + e) * W * 2, (size_t) W * 2 * sizeof(int));
+          if (best_out)
+            memcpy(best_out + ((size_t) r * n_cores + i) * 4,
+                   best.data() + ((size_t) r * j->n_ext + e) * 4, 4 * sizeof(int));
+        }
+    }
+  }
+  ramcu_job_free(c, j);
+  return rc;
+}

@@ -1,0 +1,217 @@
+"""Synthetic repeat families and a minimal .2bit writer.
+
+Everything here is *input generation* for tests and benchmarks: seeded numpy, no DP.
+A family is produced directly in the flat form the extension path consumes -- the concatenated
+per-core windows that ``loadSequenceSubsetMinimal()`` (reference sequence.c:505-923) would build
+(``sequence`` bytes: A0 C1 G2 T3 N99; one ``CORE_DTYPE`` record per core) -- and can also be
+written as ``.2bit`` + BED-6 ranges for the unchanged RAMExtend CLI.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .abi import CORE_DTYPE
+
+COMPL = np.array([3, 2, 1, 0], dtype=np.uint8)
+
+
+@dataclass
+class Family:
+    """One MSA family in flat (post-loader) form + what is needed to write it as 2bit/tsv."""
+
+    sequence: np.ndarray            # uint8 codes 0..3 / 99, concatenation of the per-core windows
+    cores: np.ndarray               # CORE_DTYPE[n], in the loader's sorted order
+    names: list = field(default_factory=list)       # 2bit sequence name per core
+    seqs: list = field(default_factory=list)        # full 2bit sequence (uint8 codes) per core
+    bed: list = field(default_factory=list)         # (name, start, end, left_flag, right_flag, strand)
+    params: dict = field(default_factory=dict)      # bandwidth / matrix / minimprovement / L ...
+
+    @property
+    def n(self) -> int:
+        return int(self.cores.size)
+
+
+def mutate(rng: np.random.Generator, anc: np.ndarray, p: float) -> np.ndarray:
+    """Per-base mutation with probability p: 80% substitution (uniform other base), 10% insertion
+    of 1-3 random bases after the base, 10% deletion."""
+    n = anc.size
+    u = rng.random(n)
+    kind = rng.random(n)
+    mut = u < p
+    sub = mut & (kind < 0.8)
+    ins = mut & (kind >= 0.8) & (kind < 0.9)
+    dele = mut & (kind >= 0.9)
+    out = anc.copy()
+    out[sub] = (anc[sub] + rng.integers(1, 4, size=int(sub.sum()))) % 4
+    reps = np.ones(n, dtype=np.int64)
+    reps[dele] = 0
+    nins = rng.integers(1, 4, size=n)
+    reps[ins] += nins[ins]
+    res = np.repeat(out, reps)
+    # positions of inserted bases: every repeat after the first of an `ins` base
+    first = np.cumsum(reps) - reps
+    is_first = np.zeros(res.size, dtype=bool)
+    is_first[first[reps > 0]] = True
+    extra = ~is_first
+    res[extra] = rng.integers(0, 4, size=int(extra.sum()))
+    return res.astype(np.uint8)
+
+
+def revcomp(x: np.ndarray) -> np.ndarray:
+    return COMPL[x[::-1]]
+
+
+def make_family(seed: int, n: int, flank: int, divergence: float = 0.15, core_len: int = 20,
+                pad: int = 500, one_sided_frac: float = 0.0, n_frac: float = 0.0,
+                params: dict | None = None) -> Family:
+    """Config-4 style family: a random ancestor of ``flank + core_len + flank`` bases; every
+    instance = independently mutated left flank + exact core + mutated right flank, 50% reverse
+    complemented, each in its own 2bit sequence ``s%07d`` with ``pad`` random bases either side.
+    ``one_sided_frac`` of the cores are extendable on one side only (config 5);
+    ``n_frac`` of the flank bases are turned into N."""
+    rng = np.random.default_rng(seed)
+    anc = rng.integers(0, 4, size=2 * flank + core_len, dtype=np.uint8)
+    left_anc, core, right_anc = anc[:flank], anc[flank:flank + core_len], anc[flank + core_len:]
+    cores = np.zeros(n, dtype=CORE_DTYPE)
+    windows, names, seqs, bed = [], [], [], []
+    off = 0
+    for i in range(n):
+        lf = mutate(rng, left_anc, divergence)
+        rf = mutate(rng, right_anc, divergence)
+        rev = bool(rng.integers(0, 2))
+        inst = np.concatenate([lf, core, rf])
+        core_start = lf.size
+        if rev:
+            inst = revcomp(inst)
+            core_start = rf.size
+        full = np.concatenate([rng.integers(0, 4, size=pad, dtype=np.uint8), inst,
+                               rng.integers(0, 4, size=pad, dtype=np.uint8)])
+        if n_frac > 0:
+            full = full.copy()
+            full[rng.random(full.size) < n_frac] = 99
+            # keep the core itself clean
+            full[pad + core_start: pad + core_start + core_len] = inst[core_start: core_start + core_len]
+        start, end = pad + core_start, pad + core_start + core_len
+        lflag = rflag = 1
+        if one_sided_frac > 0 and rng.random() < one_sided_frac:
+            if rng.integers(0, 2):
+                lflag = 0
+            else:
+                rflag = 0
+        # window logic of loadSequenceSubsetMinimal for a core alone on its sequence with
+        # max_flanking_bp >= the sequence size (sequence.c:625-743): the window reaches the
+        # sequence end on each extendable side, and stops at the core on the other side.
+        if rev:   # '-' strand: left = end side, right = start side
+            w_lo = 0 if rflag else start
+            w_hi = full.size if lflag else end
+        else:
+            w_lo = 0 if lflag else start
+            w_hi = full.size if rflag else end
+        win = full[w_lo:w_hi]
+        lower_flank = start - w_lo
+        c = cores[i]
+        c["lower_seq_bound"], c["upper_seq_bound"] = off, off + win.size - 1
+        c["left_extendable"], c["right_extendable"], c["orient"] = lflag, rflag, int(rev)
+        if rev:   # sequence.c:886-891
+            c["right_seq_pos"] = off + lower_flank
+            c["left_seq_pos"] = off + lower_flank + core_len - 1
+        else:     # sequence.c:892-897
+            c["left_seq_pos"] = off + lower_flank
+            c["right_seq_pos"] = off + lower_flank + core_len - 1
+        off += win.size
+        windows.append(win)
+        name = "s%07d" % i
+        names.append(name)
+        seqs.append(full)
+        bed.append((name, start, end, lflag, rflag, "-" if rev else "+"))
+    return Family(sequence=np.concatenate(windows), cores=cores, names=names, seqs=seqs, bed=bed,
+                  params=dict(params or {}))
+
+
+def config4(seed: int = 4, n: int = 10000, flank: int = 5000) -> Family:
+    """BASELINE.json configs[3]: 10k instances, ~15% divergence, 5 kb flanks, bandwidth 40."""
+    return make_family(seed, n, flank, 0.15, params=dict(
+        bandwidth=40, matrix="14p43g", minimprovement=30, cappenalty=-90, L=20000, when_to_stop=100))
+
+
+def matrix_for_divergence(div_pct: float):
+    """Matrix / minimprovement pick of util/extend-stk.pl:289-302."""
+    if div_pct >= 22.5:
+        return "25p43g", 3 * 9 - 3  # 25p43g default minimprovement 24 (ram_extend.c:335)
+    if div_pct >= 19:
+        return "20p43g", 27
+    if div_pct >= 16:
+        return "18p43g", 27
+    return "14p43g", 30
+
+
+def config5_specs(seed: int = 5, n_families: int = 2000):
+    """BASELINE.json configs[4]: N log-uniform in [100,10000], bandwidth in {20,40,60,80,100},
+    flank uniform in [500,5000], divergence uniform in [0.05,0.25], 10% one-sided cores."""
+    rng = np.random.default_rng(seed)
+    specs = []
+    for f in range(n_families):
+        n = int(round(10 ** rng.uniform(2, 4)))
+        bw = int(rng.choice([20, 40, 60, 80, 100]))
+        flank = int(rng.integers(500, 5001))
+        div = float(rng.uniform(0.05, 0.25))
+        matrix, minimp = matrix_for_divergence(div * 100)
+        specs.append(dict(seed=int(seed * 1000003 + f), n=n, flank=flank, divergence=div,
+                          one_sided_frac=0.10,
+                          params=dict(bandwidth=bw, matrix=matrix, minimprovement=minimp,
+                                      cappenalty=-90, L=20000, when_to_stop=100)))
+    return specs
+
+
+def family_from_spec(spec: dict) -> Family:
+    return make_family(spec["seed"], spec["n"], spec["flank"], spec["divergence"],
+                       one_sided_frac=spec.get("one_sided_frac", 0.0), params=spec["params"])
+
+
+# ------------------------------------------------------------------------------------------
+# .2bit writer / BED writer (format: SURVEY.md Appendix D; kentsrc/twoBitNew.c:250-290, 487-640)
+# ------------------------------------------------------------------------------------------
+_RAM_TO_2BIT = np.array([2, 1, 3, 0], dtype=np.uint8)   # A,C,G,T -> T0 C1 A2 G3 coding
+
+
+def write_twobit(path: str, names, seqs):
+    """Minimal UCSC .2bit (version 0): N runs become N-blocks, no mask blocks."""
+    recs = []
+    for s in seqs:
+        s = np.asarray(s, dtype=np.uint8)
+        isn = s > 3
+        d = np.diff(np.concatenate([[0], isn.astype(np.int8), [0]]))
+        nstarts = np.flatnonzero(d == 1)
+        nsizes = np.flatnonzero(d == -1) - nstarts
+        codes = np.where(isn, 0, _RAM_TO_2BIT[np.minimum(s, 3)]).astype(np.uint8)
+        padn = (-codes.size) % 4
+        codes = np.concatenate([codes, np.zeros(padn, dtype=np.uint8)]).reshape(-1, 4)
+        packed = (codes[:, 0] << 6) | (codes[:, 1] << 4) | (codes[:, 2] << 2) | codes[:, 3]
+        rec = struct.pack("<II", s.size, nstarts.size)
+        rec += nstarts.astype("<u4").tobytes() + nsizes.astype("<u4").tobytes()
+        rec += struct.pack("<II", 0, 0)
+        rec += packed.astype(np.uint8).tobytes()
+        recs.append(rec)
+    header = struct.pack("<IIII", 0x1A412743, 0, len(names), 0)
+    index_size = sum(1 + len(n) + 4 for n in names)
+    off = len(header) + index_size
+    index = b""
+    for n, rec in zip(names, recs):
+        index += struct.pack("<B", len(n)) + n.encode() + struct.pack("<I", off)
+        off += len(rec)
+    with open(path, "wb") as fh:
+        fh.write(header + index + b"".join(recs))
+
+
+def write_ranges(path: str, bed):
+    with open(path, "w") as fh:
+        for name, start, end, lflag, rflag, strand in bed:
+            fh.write(f"{name}\t{start}\t{end}\t{lflag}\t{rflag}\t{strand}\n")
+
+
+def write_family_files(fam: Family, twobit_path: str, ranges_path: str):
+    write_twobit(twobit_path, fam.names, fam.seqs)
+    write_ranges(ranges_path, fam.bed)

@@ -1,0 +1,206 @@
+// emul_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the real kernel source (repeatafterme_b200/csrc/extend_kernel.cuh) and the real host
+// flatten logic (csrc/flatten.h) with g++ against cuda_emul.h and exposes one flat C entry point,
+// so that the CPU test-suite can diff the kernel's logic against the oracle without a GPU.
+#include <pthread.h>
+#include <stdio.h>
+#include <vector>
+
+#include "cuda_emul.h"
+#include "../../repeatafterme_b200/csrc/extend_kernel.cuh"
+#include "../../repeatafterme_b200/csrc/flatten.h"
+
+thread_local dim3e threadIdx, blockIdx, blockDim, gridDim;
+thread_local EmulCta *emul_cta;
+thread_local EmulWarp *emul_warp;
+
+using namespace ramcu;
+
+typedef void (*extend_fn)(const FamDev *, const int *, int *);
+typedef void (*pack_fn)(const uint8_t *, unsigned long long, uint32_t *, uint32_t *, unsigned long long);
+
+struct LaunchArgs
+{
+  int tid, bid, block, grid;
+  EmulCta *cta;
+  extend_fn fn;
+  const FamDev *fams;
+  const int *cta_fam;
+  int *ticket;
+  // pack
+  pack_fn pfn;
+  const uint8_t *bytes;
+  unsigned long long len, n_chunks;
+  uint32_t *lib2, *libn;
+};
+
+static void *thread_main(void *p)
+{
+  LaunchArgs *a = (LaunchArgs *) p;
+  threadIdx = {(unsigned) a->tid, 0, 0};
+  blockIdx = {(unsigned) a->bid, 0, 0};
+  blockDim = {(unsigned) a->block, 1, 1};
+  gridDim = {(unsigned) a->grid, 1, 1};
+  emul_cta = a->cta;
+  emul_warp = &a->cta->warps[a->tid >> 5];
+  if (a->fn)
+    a->fn(a->fams, a->cta_fam, a->ticket);
+  else
+    a->pfn(a->bytes, a->len, a->lib2, a->libn, a->n_chunks);
+  return nullptr;
+}
+
+static int launch(LaunchArgs proto, int grid, int block)
+{
+  std::vector<EmulCta> ctas(grid);
+  std::vector<std::vector<EmulWarp>> warps(grid);
+  const int nw = (block + 31) / 32;
+  for (int b = 0; b < grid; ++b)
+  {
+    warps[b].resize(nw);
+    for (int w = 0; w < nw; ++w)
+      pthread_barrier_init(&warps[b][w].bar, nullptr, std::min(32, block - 32 * w));
+    pthread_barrier_init(&ctas[b].bar, nullptr, block);
+    ctas[b].warps = warps[b].data();
+  }
+  std::vector<LaunchArgs> args((size_t) grid * block, proto);
+  std::vector<pthread_t> th((size_t) grid * block);
+  pthread_attr_t at;
+  pthread_attr_init(&at);
+  pthread_attr_setstacksize(&at, 512 * 1024);
+  for (int b = 0; b < grid; ++b)
+    for (int t = 0; t < block; ++t)
+    {
+      LaunchArgs &a = args[(size_t) b * block + t];
+      a.tid = t;
+      a.bid = b;
+      a.block = block;
+      a.grid = grid;
+      a.cta = &ctas[b];
+      if (pthread_create(&th[(size_t) b * block + t], &at, thread_main, &a) != 0)
+        return -1;
+    }
+  for (auto &t : th)
+    pthread_join(t, nullptr);
+  return 0;
+}
+
+struct Cfg { int C, G, WS; extend_fn fn; };
+#define ECFG(C_, G_, WS_) {C_, G_, WS_, extend_kernel<C_, G_, WS_>}
+static const Cfg kCfgs[] = {
+  ECFG(11, 1, 11), ECFG(6, 2, 11), ECFG(3, 4, 11),                     // B = 5, static band
+  ECFG(29, 1, 29), ECFG(15, 2, 29), ECFG(8, 4, 29), ECFG(4, 8, 29),     // B = 14
+  ECFG(21, 4, 81), ECFG(11, 8, 81), ECFG(41, 2, 81),                    // B = 40
+  ECFG(4, 4, 0), ECFG(8, 4, 0), ECFG(16, 4, 0), ECFG(32, 4, 0), ECFG(16, 16, 0), ECFG(16, 32, 0),
+};
+
+extern "C" int emul_num_cfgs(void) { return (int) (sizeof(kCfgs) / sizeof(kCfgs[0])); }
+extern "C" void emul_cfg(int i, int *C, int *G, int *WS) { *C = kCfgs[i].C; *G = kCfgs[i].G; *WS = kCfgs[i].WS; }
+
+// Same contract as ramcu_extend() / ramcu_debug_rows() (include/ramcu.h), plus an explicit band
+// tiling (C, G, WS) and CTA size. dbg_* and forced may be NULL.
+extern "C" int emul_extend(int C, int G, int WS, int threads, const uint8_t *seq, uint64_t seq_len,
+                           int direction, int n_cores, const ramcu_core_t *cores,
+                           const ramcu_scoring_t *sc, const ramcu_params_t *pr,
+                           uint8_t *master_out, int32_t *ext_len_out, int32_t *score_add_out,
+                           ramcu_result_t *res, int dbg_nrows, const uint8_t *forced,
+                           int32_t *rows_out, int32_t *best_out, int32_t *sums_out)
+{
+  const Cfg *cfg = nullptr;
+  for (const Cfg &c : kCfgs)
+    if (c.C == C && c.G == G && c.WS == WS)
+      cfg = &c;
+  const int W = 2 * pr->bandwidth + 1;
+  if (!cfg || (WS && WS != W) || C * G < W || threads % 32 || threads > 256)
+    return -2;
+
+  // library packing through the real pack kernel
+  const unsigned long long n_chunks = (seq_len + 31) / 32;
+  std::vector<uint32_t> a2(n_chunks * 2 + 8, 0), an(n_chunks + 8, 0xffffffffu);
+  {
+    LaunchArgs p = {};
+    p.pfn = pack_library_kernel;
+    p.bytes = seq;
+    p.len = seq_len;
+    p.n_chunks = n_chunks;
+    p.lib2 = a2.data() + 4;
+    p.libn = an.data() + 4;
+    if (launch(p, 2, 32))
+      return -1;
+  }
+
+  std::vector<InstDev> inst;
+  flatten_cores(direction ? 1 : 0, n_cores, cores, seq_len, inst);
+  const int n_ext = (int) inst.size();
+  memset(res, 0, sizeof(*res));
+  res->n_extendable = n_ext;
+  if (n_ext == 0 || pr->L <= 0)
+    return -3;
+  ramcu_params_t p2 = *pr;
+  if (dbg_nrows > 0)
+  {
+    p2.L = dbg_nrows;
+    p2.when_to_stop = 1 << 30;
+  }
+  const int n_ctas = (n_ext * G + threads - 1) / threads;
+  std::vector<int> orig(n_ext), thigh(n_ext), tpos(n_ext), result(8, 0), cta_fam(n_ctas, 0);
+  for (int i = 0; i < n_ext; ++i)
+    orig[i] = inst[i].orig;
+  std::vector<unsigned char> master(p2.L + 1);
+  std::vector<unsigned long long> slots((size_t) 2 * n_ctas * 4, 0);
+  std::vector<int> drows, dbest, dsums;
+  FamDev f;
+  fill_family(f, sc, &p2, n_ext, n_ctas);
+  f.lib2 = a2.data() + 4;
+  f.libn = an.data() + 4;
+  f.inst = inst.data();
+  f.master = master.data();
+  f.thigh = thigh.data();
+  f.tpos = tpos.data();
+  f.result = result.data();
+  f.slots = slots.data();
+  if (dbg_nrows > 0)
+  {
+    drows.assign((size_t) dbg_nrows * n_ext * W * 2, 0);
+    dbest.assign((size_t) dbg_nrows * n_ext * 4, 0);
+    dsums.assign((size_t) dbg_nrows * 4, 0);
+    f.dbg_rows = drows.data();
+    f.dbg_best = dbest.data();
+    f.dbg_sums = dsums.data();
+    f.forced = forced;
+  }
+  int ticket = 0;
+  LaunchArgs a = {};
+  a.fn = cfg->fn;
+  a.fams = &f;
+  a.cta_fam = cta_fam.data();
+  a.ticket = &ticket;
+  if (launch(a, n_ctas, threads))
+    return -1;
+
+  res->extended_bp = result[0] + 1;
+  res->rows_processed = result[1];
+  res->stop_row = result[2];
+  res->max_score = result[3];
+  res->hit_limit = (result[2] >= 0 && result[2] == p2.L - 1) ? 1 : 0;
+  res->lanes_per_instance = G;
+  if (master_out)
+    memcpy(master_out, master.data(), result[1]);
+  map_results(n_cores, orig, thigh.data(), tpos.data(), ext_len_out, score_add_out);
+  for (int r = 0; r < dbg_nrows; ++r)
+  {
+    for (int e = 0; e < n_ext; ++e)
+    {
+      if (rows_out)
+        memcpy(rows_out + ((size_t) r * n_cores + orig[e]) * W * 2,
+               drows.data() + ((size_t) r * n_ext + e) * W * 2, (size_t) W * 2 * sizeof(int));
+      if (best_out)
+        memcpy(best_out + ((size_t) r * n_cores + orig[e]) * 4,
+               dbest.data() + ((size_t) r * n_ext + e) * 4, 4 * sizeof(int));
+    }
+    if (sums_out)
+      memcpy(sums_out + (size_t) r * 4, dsums.data() + (size_t) r * 4, 4 * sizeof(int));
+  }
+  return 0;
+}

@@ -1,0 +1,243 @@
+"""Test support: ctypes bindings for the checkers (oracle port, reference objects, kernel
+emulator). TEST INFRASTRUCTURE ONLY -- nothing in repeatafterme_b200/ imports this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from repeatafterme_b200.abi import CORE_DTYPE, ExtendResult, Params, Scoring, make_params
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+vp, i32, u64 = C.c_void_p, C.c_int32, C.c_uint64
+P = C.POINTER
+
+MATRICES = ("14p43g", "18p43g", "20p43g", "25p43g")
+
+
+class OracleScoring(C.Structure):
+    _fields_ = [("matrix", (C.c_int32 * 9) * 4), ("gapopen", C.c_int32), ("gapextn", C.c_int32)]
+
+    def to_product(self) -> Scoring:
+        """fold the oracle's 9 columns (ACGT acgt N) to the product's 5 (ACGT N)"""
+        m = [[self.matrix[a][b] for b in (0, 1, 2, 3, 8)] for a in range(4)]
+        return Scoring.from_array(m, self.gapopen, self.gapextn)
+
+    def m49(self) -> np.ndarray:
+        return np.array([[self.matrix[a][b] for b in range(9)] for a in range(4)], dtype=np.int32)
+
+
+class OracleResult(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("extended_bp", "rows_processed", "stop_row", "hit_limit",
+                                          "max_score", "n_extendable")]
+
+
+def _build(target_dir, target, cmd):
+    path = os.path.join(target_dir, target)
+    if not os.path.exists(path):
+        subprocess.check_call(cmd, cwd=target_dir)
+    return path
+
+
+class Oracle:
+    """oracle/liboracle.so -- this repo's CPU restatement (the checker)."""
+
+    def __init__(self):
+        path = _build(ORACLE_DIR, "liboracle.so", ["make", "-s", "oracle"])
+        self.lib = lib = C.CDLL(path)
+        lib.oracle_get_scoring.argtypes = [C.c_char_p, i32, i32, i32, P(OracleScoring)]
+        lib.oracle_nw_row.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, P(OracleScoring), i32, P(i32)]
+        lib.oracle_extend.argtypes = [i32, i32, vp, vp, P(OracleScoring), i32, i32, i32, i32, i32,
+                                      vp, vp, vp, P(OracleResult), vp]
+        lib.oracle_cell_updates.restype = C.c_double
+        lib.oracle_cell_updates.argtypes = [P(OracleResult), i32]
+
+    def scoring(self, name, rs=(1, -1, -5)) -> OracleScoring:
+        s = OracleScoring()
+        assert self.lib.oracle_get_scoring(name.encode(), rs[0], rs[1], rs[2], C.byref(s)) == 0
+        return s
+
+    def nw_row(self, direction, row_idx, cons_base, core, prev_sub, prev_gap, seq, sc, B):
+        core = np.ascontiguousarray(core, dtype=CORE_DTYPE).reshape(1)
+        ps = np.ascontiguousarray(prev_sub, dtype=np.int32)
+        pg = np.ascontiguousarray(prev_gap, dtype=np.int32)
+        cs, cg = np.zeros_like(ps), np.zeros_like(pg)
+        idx = i32(0)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        best = self.lib.oracle_nw_row(direction, row_idx, cons_base, core.ctypes.data, ps.ctypes.data,
+                                      pg.ctypes.data, cs.ctypes.data, cg.ctypes.data,
+                                      seq.ctypes.data, C.byref(sc), B, C.byref(idx))
+        return best, idx.value, cs, cg
+
+    def extend(self, direction, cores, seq, sc: OracleScoring, p: Params, trace=False):
+        cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        n = cores.size
+        master = np.zeros(max(p.L, 1), dtype=np.uint8)
+        ext_len = np.zeros(n, dtype=np.int32)
+        score_add = np.zeros(n, dtype=np.int32)
+        res = OracleResult()
+        tr = np.zeros((max(p.L, 1), 6), dtype=np.int32) if trace else None
+        self.lib.oracle_extend(direction, n, cores.ctypes.data, seq.ctypes.data, C.byref(sc),
+                               p.bandwidth, p.cappenalty, p.minimprovement, p.L, p.when_to_stop,
+                               master.ctypes.data, ext_len.ctypes.data, score_add.ctypes.data,
+                               C.byref(res), tr.ctypes.data if trace else None)
+        out = dict(extended_bp=res.extended_bp, rows_processed=res.rows_processed,
+                   stop_row=res.stop_row, hit_limit=res.hit_limit, max_score=res.max_score,
+                   n_extendable=res.n_extendable, master=master[: res.rows_processed].copy(),
+                   ext_len=ext_len, score_add=score_add)
+        if trace:
+            out["trace"] = tr[: res.rows_processed].copy()
+        return out
+
+
+class Reference:
+    """oracle/_ref/libramref.so -- the reference's own object code behind flat entry points."""
+
+    @staticmethod
+    def try_load():
+        path = os.path.join(ORACLE_DIR, "_ref", "libramref.so")
+        if not os.path.exists(path):
+            if os.path.exists("/root/reference/ram_extend.c"):
+                subprocess.check_call(["make", "-s", "ref"], cwd=ORACLE_DIR)
+            else:
+                return None
+        return Reference(path)
+
+    def __init__(self, path):
+        self.lib = lib = C.CDLL(path)
+        lib.ramref_get_scoring.argtypes = [C.c_char_p, i32, i32, i32, vp, P(i32), P(i32)]
+        lib.ramref_extend.argtypes = [i32, i32, vp, vp, u64, vp, i32, i32, i32, i32, i32, i32, i32, i32,
+                                      vp, vp, vp, P(C.c_double)]
+        lib.ramref_nw_row.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, P(i32)]
+        lib.ramref_load.argtypes = [C.c_char_p, C.c_char_p, i32, P(i32), P(u64), vp, vp, vp, vp]
+
+    def scoring(self, name, rs=(1, -1, -5)) -> OracleScoring:
+        m = np.zeros((4, 9), dtype=np.int32)
+        go, ge = i32(), i32()
+        assert self.lib.ramref_get_scoring(name.encode(), rs[0], rs[1], rs[2], m.ctypes.data,
+                                           C.byref(go), C.byref(ge)) == 0
+        s = OracleScoring()
+        for a in range(4):
+            for b in range(9):
+                s.matrix[a][b] = int(m[a, b])
+        s.gapopen, s.gapextn = go.value, ge.value
+        return s
+
+    def nw_row(self, direction, row_idx, cons_base, core, prev_sub, prev_gap, seq, sc, B):
+        core = np.ascontiguousarray(core, dtype=CORE_DTYPE).reshape(1)
+        ps = np.ascontiguousarray(prev_sub, dtype=np.int32)
+        pg = np.ascontiguousarray(prev_gap, dtype=np.int32)
+        cs, cg = np.zeros_like(ps), np.zeros_like(pg)
+        idx = i32(0)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        m = sc.m49()
+        best = self.lib.ramref_nw_row(direction, row_idx, cons_base, core.ctypes.data, ps.ctypes.data,
+                                      pg.ctypes.data, cs.ctypes.data, cg.ctypes.data, seq.ctypes.data,
+                                      m.ctypes.data, sc.gapopen, sc.gapextn, B, C.byref(idx))
+        return best, idx.value, cs, cg
+
+    def extend(self, direction, cores, seq, sc: OracleScoring, p: Params, verbose=0):
+        cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        n = cores.size
+        master = np.zeros(max(p.L, 1), dtype=np.uint8)
+        ext_len = np.zeros(n, dtype=np.int32)
+        score_add = np.zeros(n, dtype=np.int32)
+        secs = C.c_double()
+        m = sc.m49()
+        bp = self.lib.ramref_extend(direction, n, cores.ctypes.data, seq.ctypes.data, seq.size,
+                                    m.ctypes.data, sc.gapopen, sc.gapextn, p.bandwidth, p.cappenalty,
+                                    p.minimprovement, p.L, p.when_to_stop, verbose, master.ctypes.data,
+                                    ext_len.ctypes.data, score_add.ctypes.data, C.byref(secs))
+        return dict(extended_bp=bp, master=master, ext_len=ext_len, score_add=score_add,
+                    seconds=secs.value)
+
+    def load(self, twobit, ranges, max_flanking_bp):
+        n, slen = i32(), u64()
+        self.lib.ramref_load(twobit.encode(), ranges.encode(), max_flanking_bp, C.byref(n),
+                             C.byref(slen), None, None, None, None)
+        cores = np.zeros(n.value, dtype=CORE_DTYPE)
+        seq = np.zeros(slen.value, dtype=np.uint8)
+        offsets = np.zeros(n.value, dtype=np.uint64)
+        bounds = np.zeros(n.value, dtype=np.uint64)
+        self.lib.ramref_load(twobit.encode(), ranges.encode(), max_flanking_bp, C.byref(n),
+                             C.byref(slen), cores.ctypes.data, seq.ctypes.data, offsets.ctypes.data,
+                             bounds.ctypes.data)
+        return seq, cores, offsets, bounds
+
+
+class Emulator:
+    """tests/emul/libramemul.so -- the real kernel source compiled for the CPU (lock-step SIMT
+    emulation). Checks the kernel's logic without a GPU; it is not a product path."""
+
+    def __init__(self):
+        src = [os.path.join(EMUL_DIR, "emul_driver.cpp"), os.path.join(EMUL_DIR, "cuda_emul.h"),
+               os.path.join(ROOT, "repeatafterme_b200", "csrc", "extend_kernel.cuh"),
+               os.path.join(ROOT, "repeatafterme_b200", "csrc", "flatten.h")]
+        path = os.path.join(EMUL_DIR, "libramemul.so")
+        if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in src):
+            subprocess.check_call(["g++", "-std=c++17", "-O1", "-DRAMCU_EMUL", "-I.", "-fPIC", "-shared",
+                                   "-pthread", "-o", "libramemul.so", "emul_driver.cpp"], cwd=EMUL_DIR)
+        self.lib = lib = C.CDLL(path)
+        lib.emul_extend.argtypes = [i32, i32, i32, i32, vp, u64, i32, i32, vp, P(Scoring), P(Params),
+                                    vp, vp, vp, P(ExtendResult), i32, vp, vp, vp, vp]
+        lib.emul_cfg.argtypes = [i32, P(i32), P(i32), P(i32)]
+
+    def configs(self):
+        out = []
+        for i in range(self.lib.emul_num_cfgs()):
+            c, g, w = i32(), i32(), i32()
+            self.lib.emul_cfg(i, C.byref(c), C.byref(g), C.byref(w))
+            out.append((c.value, g.value, w.value))
+        return out
+
+    def configs_for(self, B):
+        W = 2 * B + 1
+        return [(c, g, w) for (c, g, w) in self.configs() if (w == W) or (w == 0 and c * g >= W)]
+
+    def extend(self, cfg, direction, cores, seq, sc: Scoring, p: Params, threads=128,
+               dbg_rows=0, forced=None):
+        cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        n, W = cores.size, 2 * p.bandwidth + 1
+        master = np.zeros(max(p.L, dbg_rows, 1) + 1, dtype=np.uint8)
+        ext_len = np.zeros(n, dtype=np.int32)
+        score_add = np.zeros(n, dtype=np.int32)
+        res = ExtendResult()
+        rows = best = sums = None
+        rp = bp = sp = fp = None
+        if dbg_rows:
+            rows = np.zeros((dbg_rows, n, W, 2), dtype=np.int32)
+            best = np.zeros((dbg_rows, n, 4), dtype=np.int32)
+            sums = np.zeros((dbg_rows, 4), dtype=np.int32)
+            rp, bp, sp = rows.ctypes.data, best.ctypes.data, sums.ctypes.data
+            if forced is not None:
+                forced = np.ascontiguousarray(forced, dtype=np.uint8)
+                fp = forced.ctypes.data
+        rc = self.lib.emul_extend(cfg[0], cfg[1], cfg[2], threads, seq.ctypes.data, seq.size, direction,
+                                  n, cores.ctypes.data, C.byref(sc), C.byref(p), master.ctypes.data,
+                                  ext_len.ctypes.data, score_add.ctypes.data, C.byref(res), dbg_rows,
+                                  fp, rp, bp, sp)
+        assert rc == 0, f"emul_extend rc={rc}"
+        return dict(extended_bp=res.extended_bp, rows_processed=res.rows_processed,
+                    stop_row=res.stop_row, hit_limit=res.hit_limit, max_score=res.max_score,
+                    n_extendable=res.n_extendable, master=master[: res.rows_processed].copy(),
+                    ext_len=ext_len, score_add=score_add, rows=rows, best=best, sums=sums)
+
+
+def compare_extend(a: dict, b: dict, what=""):
+    """bit-exact comparison of two extend results (oracle-style dicts)."""
+    for k in ("extended_bp", "rows_processed", "stop_row", "hit_limit", "max_score", "n_extendable"):
+        if k in a and k in b:
+            assert a[k] == b[k], f"{what}: {k}: {a[k]} != {b[k]}"
+    n = min(len(a["master"]), len(b["master"]))
+    if "rows_processed" in a:
+        n = a["rows_processed"]
+    assert np.array_equal(a["master"][:n], b["master"][:n]), f"{what}: consensus differs"
+    assert np.array_equal(a["ext_len"], b["ext_len"]), f"{what}: extension lengths differ"
+    assert np.array_equal(a["score_add"], b["score_add"]), f"{what}: score increments differ"
