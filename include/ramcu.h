@@ -82,7 +82,9 @@ typedef struct
   int32_t L;               /* max extension length                                            */
   int32_t when_to_stop;    /* WHEN_TO_STOP global (ram_extend.c:61,249)                        */
   int32_t lanes_per_instance; /* 0 = auto; else force 1,2,4,8,16,32 (tuning/tests)            */
-  int32_t reserved[2];
+  int32_t concurrent_instances; /* hint: instances of OTHER families expected to share the GPU
+                                 * with this one (ramcu_batch_run); 0 = runs alone            */
+  int32_t reserved[1];
 } ramcu_params_t;
 
 typedef struct

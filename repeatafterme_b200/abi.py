@@ -68,7 +68,8 @@ class Params(C.Structure):
         ("L", C.c_int32),
         ("when_to_stop", C.c_int32),
         ("lanes_per_instance", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("concurrent_instances", C.c_int32),
+        ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -91,11 +92,12 @@ class ExtendResult(C.Structure):
 
 
 def make_params(bandwidth=14, cappenalty=-90, minimprovement=27, L=10000, when_to_stop=100,
-                lanes_per_instance=0) -> Params:
+                lanes_per_instance=0, concurrent_instances=0) -> Params:
     """Defaults are those of the RAMExtend CLI (ram_extend.c:246-249, 301-344)."""
     p = Params()
     p.bandwidth, p.cappenalty, p.minimprovement, p.L, p.when_to_stop, p.lanes_per_instance = (
         bandwidth, cappenalty, minimprovement, L, when_to_stop, lanes_per_instance)
+    p.concurrent_instances = concurrent_instances
     return p
 
 

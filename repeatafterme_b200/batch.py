@@ -1,0 +1,94 @@
+"""Family batches: what util/extend-stk.pl does with one RAMExtend process per family
+(extend-stk.pl:242-371) -- here many independent families share one CUDA context, and families
+are sharded across the GPUs of a box with no communication between them.
+
+Per family this runs exactly the two calls the reference's main() makes (ram_extend.c:424-427,
+506-509): the right pass, then the left pass. The overlap-avoidance step between the passes
+(ram_extend.c:445-499) only narrows bounds of cores that share a 2bit sequence; callers that have
+such families pass ``between_passes`` (the unchanged CLI keeps running the reference's own loop).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .abi import RamCu, Scoring, make_params
+
+
+def family_cost(n: int, bandwidth: int, flank: int) -> float:
+    """LPT weight N * (2B+1) * flank."""
+    return float(n) * (2 * bandwidth + 1) * max(flank, 1)
+
+
+def lpt_shard(costs, world_size: int):
+    """Longest-processing-time-first partition of families over ranks. Returns a list of index
+    lists, one per rank; every family appears exactly once."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * world_size
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        shards[r].append(i)
+        loads[r] += costs[i]
+    return shards
+
+
+@dataclass
+class FamilyResult:
+    right: dict = field(default_factory=dict)
+    left: dict = field(default_factory=dict)
+
+    @property
+    def cell_updates(self) -> float:
+        cu = 0.0
+        for d in (self.right, self.left):
+            if d:
+                cu += d["rows_processed"] * d["n_extendable"] * (2 * d["bandwidth"] + 1) * 4.0
+        return cu
+
+
+def _as_dict(res, master, ext_len, score_add, bandwidth):
+    d = res.as_dict()
+    d.update(master=master, ext_len=ext_len, score_add=score_add, bandwidth=bandwidth)
+    return d
+
+
+def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
+    """Extend a list of families (objects with .sequence, .cores, .params as in synth.Family).
+    Host buffers in, host results out: library upload, right pass of every family as one batch,
+    fetch, left pass of every family as one batch, fetch."""
+    libs, scs, prs = [], [], []
+    total = sum(int(f.cores.size) for f in fams)
+    for f in fams:
+        p = dict(f.params)
+        matrix = p.pop("matrix", "20p43g")
+        rs = p.pop("rs", (1, -1, -5))
+        sc = rc.scoring(matrix, rs)
+        if concurrent_hint and len(fams) > 1:
+            p["concurrent_instances"] = total - int(f.cores.size)
+        scs.append(sc)
+        prs.append(make_params(**p))
+        libs.append(rc.upload_library(f.sequence))
+    results = [FamilyResult() for _ in fams]
+    try:
+        for direction in (1, 0):
+            jobs = [rc.job_create(libs[i], direction, f.cores, scs[i], prs[i]) for i, f in enumerate(fams)]
+            if len(jobs) == 1:
+                rc.job_run(jobs[0])
+            else:
+                rc.batch_run(jobs)
+            for i, f in enumerate(fams):
+                out = _as_dict(*rc.job_fetch(jobs[i], f.cores.size, prs[i].L), prs[i].bandwidth)
+                if direction:
+                    results[i].right = out
+                else:
+                    results[i].left = out
+                rc.job_free(jobs[i])
+            if direction and between_passes is not None:
+                for i, f in enumerate(fams):
+                    between_passes(f, results[i].right)
+    finally:
+        for h in libs:
+            rc.free_library(h)
+    return results

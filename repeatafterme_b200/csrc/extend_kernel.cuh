@@ -36,7 +36,7 @@ constexpr int kNegInf = -1050000000;  // "no carry": below every reachable cell 
                                       // 2*kNegInf still fits in int32
 constexpr int kBig = 1 << 28;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kMaxWarps = 8;          // CTA size <= 256 threads
+constexpr int kMaxWarps = 32;         // CTA size <= 1024 threads
 
 // One extendable instance of a family, in the direction being extended (device copy).
 struct InstDev
@@ -59,7 +59,7 @@ struct FamDev
   int *thigh;             // out: trimmed_sequence_high_score      (per extendable instance)
   int *tpos;              // out: trimmed_sequence_high_score_pos
   int *result;            // out: [0] max_row [1] rows_processed [2] stop_row [3] max_ext
-  unsigned long long *slots;    // [2][n_ctas][4] (tag<<32 | partial sum) grid exchange
+  unsigned long long *slots;    // [L][4] per-column (count << 48 | sum) accumulators, zeroed
   const unsigned char *forced;  // debug: forced consensus per row (or NULL)
   int *dbg_rows;          // debug: [rows][n_ext][W][2]
   int *dbg_best;          // debug: [rows][n_ext][4]
@@ -226,39 +226,31 @@ __device__ __forceinline__ void band_pass(int (&Sp)[C], int (&Gp)[C], const int 
     gout[a] = gprev[a];
 }
 
-// Grid-level exchange of the four per-candidate partial sums of one column between the CTAs of
-// a family. Every CTA publishes (tag, partial) pairs as single 64-bit words, then warp 0 of
-// every CTA gathers all of them. The flag travels with the data, so one L2 round trip suffices
-// and no fence is needed; slots are double-buffered by column parity.
-__device__ __forceinline__ void grid_exchange(unsigned long long *slots, const int n_ctas,
-                                              const int cta_in_fam, const int par,
-                                              const unsigned tag, unsigned (&sums)[4],
-                                              const int lane)
+// Grid-level reduction of the four per-candidate partial sums of column r between the CTAs of a
+// family. Column r owns four 64-bit accumulators (zeroed before the launch); every CTA adds
+// (1 << 48 | partial) with one RED per candidate, so the arrival count travels in the same word
+// as the data: a reader that sees count == n_ctas has the complete sum in the low 32 bits
+// (mod 2^32, exactly the reference's int arithmetic). One L2 round trip, no fence, no reset, and
+// only warp 0 of each CTA spends issue slots on it.
+__device__ __forceinline__ void grid_exchange(unsigned long long *acc_row, const int n_ctas,
+                                              unsigned (&sums)[4], const int lane)
 {
-  unsigned long long *base = slots + (size_t) par * n_ctas * 4;
+  unsigned lo = 0;
   if (lane < 4)
   {
     const unsigned mine = (unsigned) sel4(lane, (int) sums[0], (int) sums[1], (int) sums[2], (int) sums[3]);
-    st_relaxed_u64(base + cta_in_fam * 4 + lane, ((unsigned long long) tag << 32) | mine);
-  }
-  unsigned acc = 0;
-  for (int i = lane; i < n_ctas * 4; i += 32)
-  {
+    atomicAdd(acc_row + lane, (1ull << 48) | (unsigned long long) mine);
     unsigned long long v;
     do
     {
-      v = ld_relaxed_u64(base + i);
-    } while ((unsigned) (v >> 32) != tag);
-    acc += (unsigned) v;
+      v = ld_relaxed_u64(acc_row + lane);
+    } while ((int) (v >> 48) != n_ctas);
+    lo = (unsigned) v;
   }
-  // lanes with equal (lane & 3) hold partial sums of candidate (lane & 3)
-  acc += __shfl_xor_sync(kFull, acc, 4);
-  acc += __shfl_xor_sync(kFull, acc, 8);
-  acc += __shfl_xor_sync(kFull, acc, 16);
-  sums[0] = __shfl_sync(kFull, acc, 0);
-  sums[1] = __shfl_sync(kFull, acc, 1);
-  sums[2] = __shfl_sync(kFull, acc, 2);
-  sums[3] = __shfl_sync(kFull, acc, 3);
+  sums[0] = __shfl_sync(kFull, lo, 0);
+  sums[1] = __shfl_sync(kFull, lo, 1);
+  sums[2] = __shfl_sync(kFull, lo, 2);
+  sums[3] = __shfl_sync(kFull, lo, 3);
 }
 
 // per-CTA shared state: score LUT, per-warp partial column sums, broadcast sums, logical CTA id
@@ -270,8 +262,8 @@ struct SharedBlk
   int cta;
 };
 
-template <int C, int G, int WS>
-__global__ void __launch_bounds__(256)
+template <int C, int G, int WS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, int *ticket)
 {
   static_assert((G & (G - 1)) == 0 && G >= 1 && G <= 32, "G must be a power of two <= 32");
@@ -311,9 +303,13 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   const unsigned char *forced = F->forced;
   int *dbg_rows = F->dbg_rows;
 
-  const int inst = cta_in_fam * (blockDim.x / G) + (int) threadIdx.x / G;
-  const bool valid = inst < n_ext;
-  const InstDev I = F->inst[valid ? inst : n_ext - 1];
+  // balanced partition of the family's instances over its CTAs (n_ctas <= n_ext)
+  const int first = (int) ((long long) cta_in_fam * n_ext / n_ctas);
+  const int next = (int) ((long long) (cta_in_fam + 1) * n_ext / n_ctas);
+  const int grp = (int) threadIdx.x / G;
+  const bool valid = grp < next - first;
+  const int inst = valid ? first + grp : next - 1;   // padding lanes shadow the last instance
+  const InstDev I = F->inst[inst];
   const uint32_t *lib2 = F->lib2, *libn = F->libn;
   const int tmin = I.tmin, tmax = I.tmax;
 
@@ -489,7 +485,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       {
         if (warp == 0)
         {
-          grid_exchange(F->slots, n_ctas, cta_in_fam, par, (unsigned) (r + 1), sums, lane);
+          grid_exchange(F->slots + (size_t) r * 4, n_ctas, sums, lane);
           if (lane == 0)
             s_bcast[par] = make_int4((int) sums[0], (int) sums[1], (int) sums[2], (int) sums[3]);
         }

@@ -53,15 +53,27 @@ struct KernelCfg
   int B;    // bandwidth this instantiation is specialised for (-1 = any, runtime W)
   int C;    // cells per lane
   int G;    // lanes per instance
+  int maxt; // largest CTA size (threads) supported
   extend_fn fn;
-  int regs;            // filled at init
-  int max_cta_per_sm;  // at kThreads threads per CTA, filled at init
+  int regs; // filled at init
 };
 
-static const int kThreads = 128;
+// how a family is laid out on the grid
+struct Plan
+{
+  int n_ctas;
+  int threads;  // CTA size for a launch of this family alone
+};
 
-#define RAMCU_CFG(B_, C_, G_) {B_, C_, G_, extend_kernel<C_, G_, 2 * B_ + 1>, 0, 0}
-#define RAMCU_GEN(C_, G_) {-1, C_, G_, extend_kernel<C_, G_, 0>, 0, 0}
+static const int kBatchThreads = 128;   // CTA size used when many families share a launch
+
+// MAXT = largest CTA the instantiation supports; it caps registers per thread at 65536 / MAXT
+constexpr int maxt_for(int C)
+{
+  return C <= 8 ? 768 : C <= 13 ? 640 : C <= 16 ? 512 : C <= 21 ? 384 : C <= 32 ? 320 : 256;
+}
+#define RAMCU_CFG(B_, C_, G_) {B_, C_, G_, maxt_for(C_), extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_)>, 0}
+#define RAMCU_GEN(C_, G_) {-1, C_, G_, maxt_for(C_), extend_kernel<C_, G_, 0, maxt_for(C_)>, 0}
 
 static KernelCfg g_cfgs[] = {
   // RAMExtend default (ram_extend.c:247)
@@ -105,7 +117,9 @@ struct ramcu_job
   ramcu_scoring_t sc;
   ramcu_params_t pr;
   const KernelCfg *cfg;
-  int n_ctas;
+  int n_ctas;                 // > 0 when there is anything to launch (== solo.n_ctas)
+  Plan solo;                  // layout for ramcu_job_run
+  int batch_ctas;             // layout for ramcu_batch_run (kBatchThreads per CTA)
   std::vector<int> orig;      // ext index -> core index
   FamDev fam;                 // host copy (device pointers inside)
   // device
@@ -162,9 +176,6 @@ extern "C" int ramcu_init(int device, ramcu_ctx **out)
                   cudaGetErrorString(e));
     }
     g_cfgs[i].regs = fa.numRegs;
-    int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *) g_cfgs[i].fn, kThreads, 0));
-    g_cfgs[i].max_cta_per_sm = nb;
   }
   *out = c;
   return RAMCU_OK;
@@ -315,8 +326,91 @@ extern "C" int ramcu_library_free(ramcu_ctx *c, ramcu_library *lib)
 // ------------------------------------------------------------------------------------------
 // jobs
 // ------------------------------------------------------------------------------------------
+static int round32(long long x) { return (int) (((x + 31) / 32) * 32); }
+
+// CTA size needed when n_ext instances are split evenly over n_ctas CTAs
+static int threads_for(int n_ext, int n_ctas, int G)
+{
+  const int mx = (n_ext + n_ctas - 1) / n_ctas;
+  return round32((long long) mx * G);
+}
+
+static int ctas_per_sm(const KernelCfg *k, int threads)
+{
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *) k->fn, threads, 0) != cudaSuccess)
+    return 0;
+  return nb;
+}
+
+// Layout of one family launched on its own: a single CTA when it fits (no grid exchange at all),
+// else ~128-thread CTAs on distinct SMs, else the same number of equally loaded CTAs on every SM
+// (the column time is set by the most loaded SM, and every CTA waits for it).
+static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int n_ext, Plan *p)
+{
+  const long long lanes = (long long) n_ext * k->G;
+  const int sm = c->sm_count;
+  if (lanes <= k->maxt)
+  {
+    p->n_ctas = 1;
+    p->threads = round32(lanes);
+    return true;
+  }
+  if (lanes <= (long long) sm * 128)
+  {
+    p->n_ctas = (int) std::min<long long>((lanes + 127) / 128, n_ext);
+    p->threads = threads_for(n_ext, p->n_ctas, k->G);
+    return p->threads <= k->maxt;
+  }
+  for (int per_sm = 1; per_sm <= 16; ++per_sm)
+  {
+    const long long n = (long long) sm * per_sm;
+    if (n > n_ext)
+      break;
+    const int t = threads_for(n_ext, (int) n, k->G);
+    if (t > k->maxt)
+      continue;
+    if (ctas_per_sm(k, t) < per_sm)
+      continue;
+    p->n_ctas = (int) n;
+    p->threads = t;
+    return true;
+  }
+  return false;
+}
+
+// Layout when the family shares a launch with others: fixed CTA size.
+static bool plan_batch(const ramcu_ctx *c, const KernelCfg *k, int n_ext, int *n_ctas)
+{
+  const long long lanes = (long long) n_ext * k->G;
+  long long n = std::min<long long>((lanes + kBatchThreads - 1) / kBatchThreads, n_ext);
+  while (n < n_ext && threads_for(n_ext, (int) n, k->G) > kBatchThreads)
+    ++n;
+  if (threads_for(n_ext, (int) n, k->G) > kBatchThreads)
+    return false;
+  if (n > (long long) ctas_per_sm(k, kBatchThreads) * c->sm_count)
+    return false;   // its CTAs could not all be resident: the column exchange would deadlock
+  *n_ctas = (int) n;
+  return true;
+}
+
+// Rough cycles per column of a family running alone (tuned on B200): a warp
+// executes about C*35 + 200 + 25*log2(G) instructions per row; one warp alone issues one every
+// ~4.5 cycles (dependent max-plus chains), a loaded scheduler one every ~2.2 cycles.
+static double solo_cost(const ramcu_ctx *c, const KernelCfg *k, int n_ext, const Plan &p)
+{
+  int lg = 0;
+  while ((1 << lg) < k->G)
+    ++lg;
+  const double instr = k->C * 35.0 + 200.0 + 25.0 * lg;
+  const double warps = (double) p.n_ctas * (p.threads / 32);
+  const double per_sched = std::max(1.0, std::ceil(warps / (c->sm_count * 4.0)));
+  const double sync = p.n_ctas > 1 ? 2500.0 : 0.0;
+  return std::max(instr * 4.5, per_sched * instr * 2.2) + sync;
+}
+
 static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force_G,
-                                 long long other_threads)
+                                 int concurrent_instances, Plan *solo, int *batch_ctas)
 {
   const int W = 2 * B + 1;
   std::vector<const KernelCfg *> cand;
@@ -329,41 +423,41 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force
           (g_cfgs[i].G - 1) * g_cfgs[i].C < W)
         cand.push_back(&g_cfgs[i]);
   if (cand.empty())
-    for (int i = 0; i < g_ncfg; ++i)  // narrow bands: last lanes may be entirely padding
+    for (int i = 0; i < g_ncfg; ++i)  // narrow bands: trailing lanes may be entirely padding
       if (g_cfgs[i].B < 0 && g_cfgs[i].C * g_cfgs[i].G >= W)
       {
         cand.push_back(&g_cfgs[i]);
         break;
       }
-  if (cand.empty())
-    return nullptr;
   std::sort(cand.begin(), cand.end(),
             [](const KernelCfg *a, const KernelCfg *b) { return a->G < b->G; });
-  auto fits = [&](const KernelCfg *k) {
-    const long long ctas = ((long long) n_ext * k->G + kThreads - 1) / kThreads;
-    return ctas <= (long long) k->max_cta_per_sm * c->sm_count;
-  };
-  if (force_G > 0)
-  {
-    for (const KernelCfg *k : cand)
-      if (k->G == force_G && fits(k))
-        return k;
-    return nullptr;
-  }
-  // Fewest lanes per instance (least cross-lane overhead) that still gives the GPU enough
-  // threads; families that fill the device on their own keep G small.
-  const long long target = (long long) c->sm_count * 256;
   const KernelCfg *best = nullptr;
+  double best_cost = 0;
+  const bool crowded = concurrent_instances >= c->sm_count * 128;
   for (const KernelCfg *k : cand)
   {
-    if (!fits(k))
+    if (force_G > 0 && k->G != force_G)
       continue;
-    best = k;
-    if ((long long) n_ext * k->G + other_threads >= target)
-      break;
+    Plan p;
+    int nb = 0;
+    if (!plan_solo(c, k, n_ext, &p))
+      continue;
+    if (!plan_batch(c, k, n_ext, &nb))
+      nb = 0;   // too large to share a launch: ramcu_batch_run launches it on its own
+    // a crowded device is throughput bound: fewest lanes per instance = fewest instructions
+    const double cost = crowded ? (double) k->G : solo_cost(c, k, n_ext, p);
+    if (!best || cost < best_cost)
+    {
+      best = k;
+      best_cost = cost;
+      *solo = p;
+      *batch_ctas = nb;
+    }
   }
   return best;
 }
+
+static size_t slots_bytes(int L) { return ((size_t) L + 1) * 4 * sizeof(unsigned long long); }
 
 static void free_job_device(ramcu_job *j)
 {
@@ -424,7 +518,8 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
   j->n_ctas = 0;
   if (j->n_ext > 0 && pr->L > 0)
   {
-    j->cfg = pick_cfg(c, B, j->n_ext, pr->lanes_per_instance, 0);
+    j->cfg = pick_cfg(c, B, j->n_ext, pr->lanes_per_instance, pr->concurrent_instances, &j->solo,
+                      &j->batch_ctas);
     if (!j->cfg)
     {
       delete j;
@@ -432,7 +527,8 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
                   "no band tiling for bandwidth %d with %d instances fits this device "
                   "(lanes_per_instance=%d)", B, (int) inst.size(), pr->lanes_per_instance);
     }
-    j->n_ctas = (int) (((long long) j->n_ext * j->cfg->G + kThreads - 1) / kThreads);
+    j->n_ctas = j->solo.n_ctas;
+    const int max_ctas = std::max(j->solo.n_ctas, j->batch_ctas);
 
     const int W = 2 * B + 1;
     CK(cudaMalloc(&j->d_inst, inst.size() * sizeof(InstDev)));
@@ -442,10 +538,10 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     CK(cudaMalloc(&j->d_thigh, inst.size() * sizeof(int)));
     CK(cudaMalloc(&j->d_tpos, inst.size() * sizeof(int)));
     CK(cudaMalloc(&j->d_result, 8 * sizeof(int)));
-    CK(cudaMalloc(&j->d_slots, (size_t) 2 * j->n_ctas * 4 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&j->d_slots, slots_bytes(pr->L)));
     CK(cudaMalloc(&j->d_fam, sizeof(FamDev)));
-    CK(cudaMalloc(&j->d_cta_fam, j->n_ctas * sizeof(int)));
-    CK(cudaMemsetAsync(j->d_cta_fam, 0, j->n_ctas * sizeof(int), c->stream));
+    CK(cudaMalloc(&j->d_cta_fam, max_ctas * sizeof(int)));
+    CK(cudaMemsetAsync(j->d_cta_fam, 0, max_ctas * sizeof(int), c->stream));
     if (dbg_rows > 0)
     {
       CK(cudaMalloc(&j->d_dbg_rows, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int)));
@@ -489,8 +585,9 @@ extern "C" int ramcu_job_create(ramcu_ctx *c, ramcu_library *lib, int direction,
 static int launch_single(ramcu_ctx *c, ramcu_job *j)
 {
   CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(int), c->stream));
-  CK(cudaMemsetAsync(j->d_slots, 0, (size_t) 2 * j->n_ctas * 4 * sizeof(unsigned long long), c->stream));
-  j->cfg->fn<<<j->n_ctas, kThreads, 0, c->stream>>>(j->d_fam, j->d_cta_fam, c->d_ticket);
+  if (j->n_ctas > 1)
+    CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->pr.L), c->stream));
+  j->cfg->fn<<<j->solo.n_ctas, j->solo.threads, 0, c->stream>>>(j->d_fam, j->d_cta_fam, c->d_ticket);
   CK(cudaGetLastError());
   return RAMCU_OK;
 }
@@ -622,7 +719,7 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
       return fail(RAMCU_ERR_ARG, "ramcu_batch_run: jobs[%d] == NULL", i);
     jobs[i]->ran = true;
     jobs[i]->timed = false;
-    if (jobs[i]->n_ctas > 0)
+    if (jobs[i]->n_ctas > 0 && jobs[i]->batch_ctas > 0)
       order.push_back(i);
   }
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
@@ -633,6 +730,13 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
     return wa > wb;
   });
   CK(cudaEventRecord(c->ev0, c->stream));
+  for (int i = 0; i < n_jobs; ++i)
+    if (jobs[i]->n_ctas > 0 && jobs[i]->batch_ctas == 0)
+    {
+      int rc = launch_single(c, jobs[i]);
+      if (rc)
+        return rc;
+    }
   size_t p = 0;
   while (p < order.size())
   {
@@ -645,11 +749,12 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
       ramcu_job *j = jobs[order[q]];
       FamDev f = j->fam;
       f.cta0 = (int) cta_fam.size();
-      for (int k = 0; k < j->n_ctas; ++k)
+      f.n_ctas = j->batch_ctas;
+      for (int k = 0; k < j->batch_ctas; ++k)
         cta_fam.push_back((int) fams.size());
       fams.push_back(f);
-      CK(cudaMemsetAsync(j->d_slots, 0, (size_t) 2 * j->n_ctas * 4 * sizeof(unsigned long long),
-                         c->stream));
+      if (j->batch_ctas > 1)
+        CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->pr.L), c->stream));
       ++q;
     }
     FamDev *d_fams = nullptr;
@@ -660,14 +765,14 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
     CK(cudaMemcpyAsync(d_map, cta_fam.data(), cta_fam.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(int), c->stream));
     // pageable sources: the copies above have completed on return, so the vectors may go away
-    cfg->fn<<<(int) cta_fam.size(), kThreads, 0, c->stream>>>(d_fams, d_map, c->d_ticket);
+    cfg->fn<<<(int) cta_fam.size(), kBatchThreads, 0, c->stream>>>(d_fams, d_map, c->d_ticket);
     CK(cudaGetLastError());
     CK(cudaFreeAsync(d_fams, c->stream));
     CK(cudaFreeAsync(d_map, c->stream));
     p = q;
   }
   CK(cudaEventRecord(c->ev1, c->stream));
-  for (int i : order)
+  for (int i = 0; i < n_jobs; ++i)
     jobs[i]->timed = true;
   return RAMCU_OK;
 }

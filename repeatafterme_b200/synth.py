@@ -61,7 +61,8 @@ def mutate(rng: np.random.Generator, anc: np.ndarray, p: float) -> np.ndarray:
 
 
 def revcomp(x: np.ndarray) -> np.ndarray:
-    return COMPL[x[::-1]]
+    x = np.asarray(x, dtype=np.uint8)[::-1]
+    return np.where(x > 3, 99, COMPL[np.minimum(x, 3)]).astype(np.uint8)
 
 
 def make_family(seed: int, n: int, flank: int, divergence: float = 0.15, core_len: int = 20,
@@ -215,3 +216,35 @@ def write_ranges(path: str, bed):
 def write_family_files(fam: Family, twobit_path: str, ranges_path: str):
     write_twobit(twobit_path, fam.names, fam.seqs)
     write_ranges(ranges_path, fam.bed)
+
+
+def read_twobit(path: str):
+    """Minimal .2bit reader (version 0, little endian): returns (names, [uint8 code arrays]) with
+    A0 C1 G2 T3 and 99 inside N-blocks (soft-mask blocks are ignored, as RAMExtend upper-cases)."""
+    data = open(path, "rb").read()
+    sig, version, count, _ = struct.unpack_from("<IIII", data, 0)
+    assert sig == 0x1A412743 and version == 0, "unsupported .2bit"
+    pos = 16
+    names, offs = [], []
+    for _ in range(count):
+        ln = data[pos]
+        names.append(data[pos + 1: pos + 1 + ln].decode())
+        offs.append(struct.unpack_from("<I", data, pos + 1 + ln)[0])
+        pos += 1 + ln + 4
+    two2ram = np.array([3, 1, 0, 2], dtype=np.uint8)   # T0 C1 A2 G3 -> A0 C1 G2 T3
+    seqs = []
+    for off in offs:
+        size, nb = struct.unpack_from("<II", data, off)
+        p = off + 8
+        nstarts = np.frombuffer(data, "<u4", nb, p)
+        nsizes = np.frombuffer(data, "<u4", nb, p + 4 * nb)
+        p += 8 * nb
+        mb = struct.unpack_from("<I", data, p)[0]
+        p += 4 + 8 * mb + 4
+        packed = np.frombuffer(data, np.uint8, (size + 3) // 4, p)
+        codes = np.stack([(packed >> 6) & 3, (packed >> 4) & 3, (packed >> 2) & 3, packed & 3], axis=1)
+        s = two2ram[codes.reshape(-1)[:size]].copy()
+        for a, b in zip(nstarts, nsizes):
+            s[a:a + b] = 99
+        seqs.append(s)
+    return names, seqs

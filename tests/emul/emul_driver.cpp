@@ -87,7 +87,7 @@ static int launch(LaunchArgs proto, int grid, int block)
 }
 
 struct Cfg { int C, G, WS; extend_fn fn; };
-#define ECFG(C_, G_, WS_) {C_, G_, WS_, extend_kernel<C_, G_, WS_>}
+#define ECFG(C_, G_, WS_) {C_, G_, WS_, extend_kernel<C_, G_, WS_, 1024>}
 static const Cfg kCfgs[] = {
   ECFG(11, 1, 11), ECFG(6, 2, 11), ECFG(3, 4, 11),                     // B = 5, static band
   ECFG(29, 1, 29), ECFG(15, 2, 29), ECFG(8, 4, 29), ECFG(4, 8, 29),     // B = 14
@@ -112,7 +112,7 @@ extern "C" int emul_extend(int C, int G, int WS, int threads, const uint8_t *seq
     if (c.C == C && c.G == G && c.WS == WS)
       cfg = &c;
   const int W = 2 * pr->bandwidth + 1;
-  if (!cfg || (WS && WS != W) || C * G < W || threads % 32 || threads > 256)
+  if (!cfg || (WS && WS != W) || C * G < W || threads % 32 || threads > 1024)
     return -2;
 
   // library packing through the real pack kernel
@@ -143,12 +143,18 @@ extern "C" int emul_extend(int C, int G, int WS, int threads, const uint8_t *seq
     p2.L = dbg_nrows;
     p2.when_to_stop = 1 << 30;
   }
-  const int n_ctas = (n_ext * G + threads - 1) / threads;
+  const int n_ctas = std::min(n_ext, (n_ext * G + threads - 1) / threads);
+  {
+    int mx = 0;
+    for (int i = 0; i < n_ctas; ++i)
+      mx = std::max(mx, (int) ((long long) (i + 1) * n_ext / n_ctas) - (int) ((long long) i * n_ext / n_ctas));
+    threads = ((mx * G + 31) / 32) * 32;
+  }
   std::vector<int> orig(n_ext), thigh(n_ext), tpos(n_ext), result(8, 0), cta_fam(n_ctas, 0);
   for (int i = 0; i < n_ext; ++i)
     orig[i] = inst[i].orig;
   std::vector<unsigned char> master(p2.L + 1);
-  std::vector<unsigned long long> slots((size_t) 2 * n_ctas * 4, 0);
+  std::vector<unsigned long long> slots((size_t) (p2.L + 1) * 4, 0);
   std::vector<int> drows, dbest, dsums;
   FamDev f;
   fill_family(f, sc, &p2, n_ext, n_ctas);

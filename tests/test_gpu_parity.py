@@ -1,0 +1,227 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (libramcu.so), against the oracle,
+the committed reference outputs (tests/golden) and size-independent properties at full size.
+Bit-exact everywhere: the path is int32 max-plus."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from repeatafterme_b200 import batch, synth
+from repeatafterme_b200.abi import CORE_DTYPE, RamCuError, make_params
+from tests import golden_io as gio
+from tests import support
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _got(res, master, ext_len, score_add):
+    return dict(res.as_dict(), master=master, ext_len=ext_len, score_add=score_add)
+
+
+@pytest.mark.parametrize("name", gio.flat_case_names())
+def test_golden_flat_cases_every_tiling(ramcu, oracle, name):
+    """reference outputs (golden) == CUDA path for the automatic tiling and every forced one"""
+    case = gio.load_flat(name)
+    sc = gio.oracle_scoring_for(case, oracle).to_product()
+    lib = ramcu.upload_library(case["sequence"])
+    ran = 0
+    try:
+        for G in (0, 1, 2, 4, 8, 16, 32):
+            p = gio.params_for(case, lanes_per_instance=G)
+            for d in (1, 0):
+                try:
+                    got = _got(*ramcu.extend(lib, d, case["cores"], sc, p))
+                except RamCuError as ex:
+                    assert "no band tiling" in str(ex), ex
+                    continue
+                gio.check_against_golden(case, d, got, f"{name} G={G} dir={d}")
+                ran += 1
+    finally:
+        ramcu.free_library(lib)
+    assert ran >= 4
+
+
+def test_unit_vectors_through_debug_rows(ramcu, oracle):
+    """bnw_extend.c:1384-1651 replayed through the kernel (forced consensus): every band row, the
+    reciprocity of the two libraries and the known-answer row 6 (bnw_extend.c:1566-1567)"""
+    u = gio.load_unit()
+    B = u["bandwidth"]
+    sc = oracle.scoring(u["matrix"]).to_product()
+    rows = {}
+    for side, direction in (("left", 0), ("right", 1)):
+        seq = np.array(u[f"p_{side}"], dtype=np.uint8)
+        cores = np.zeros(3, dtype=CORE_DTYPE)
+        for n in range(3):
+            l, r, lo, hi, orient = u[f"{side}_cores"][n]
+            cores[n]["left_seq_pos"], cores[n]["right_seq_pos"] = l, r
+            cores[n]["lower_seq_bound"], cores[n]["upper_seq_bound"], cores[n]["orient"] = lo, hi, orient
+            cores[n]["left_extendable"] = cores[n]["right_extendable"] = 1
+        nrows = len(u["cons_base"])
+        lib = ramcu.upload_library(seq)
+        r, best, sums = ramcu.debug_rows(lib, direction, cores, sc, make_params(bandwidth=B, L=nrows),
+                                         nrows, forced=u["cons_base"])
+        ramcu.free_library(lib)
+        rows[side] = r
+        for n in range(3):
+            for row in range(nrows):
+                want = u["reference_rows"][side][n][row]
+                assert r[row, n, :, 0].tolist() == want["sub"] and r[row, n, :, 1].tolist() == want["gap"]
+                assert best[row, n, u["cons_base"][row]] == want["best"]
+    assert np.array_equal(rows["left"], rows["right"])
+    assert rows["right"][6, 0, :, 1].tolist() == u["final_right_gap"]
+    assert rows["right"][6, 0, :, 0].tolist() == u["final_right_sub"]
+
+
+@pytest.mark.parametrize("seed,n,flank,B,matrix,kw", [
+    (101, 300, 400, 40, "14p43g", dict(one_sided_frac=0.1, n_frac=0.005)),
+    (102, 700, 300, 14, "20p43g", dict()),
+    (103, 150, 250, 100, "25p43g", dict(one_sided_frac=0.2)),
+    (104, 64, 200, 7, "18p43g", dict(pad=0)),
+    (105, 200, 300, 33, "14p43g", dict(n_frac=0.05)),
+    (106, 257, 200, 80, "18p43g", dict(pad=5)),
+])
+def test_random_families_vs_oracle(ramcu, oracle, seed, n, flank, B, matrix, kw):
+    fam = synth.make_family(seed, n, flank, 0.15, **kw)
+    osc = oracle.scoring(matrix)
+    lib = ramcu.upload_library(fam.sequence)
+    try:
+        for L in (20000, flank // 2):
+            p = make_params(bandwidth=B, minimprovement=27, L=L)
+            for d in (1, 0):
+                want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+                got = _got(*ramcu.extend(lib, d, fam.cores, osc.to_product(), p))
+                support.compare_extend(want, got, f"seed={seed} L={L} dir={d}")
+    finally:
+        ramcu.free_library(lib)
+
+
+def test_rows_and_sums_vs_oracle_trace(ramcu, oracle):
+    """per-row column sums / chosen base (the argmax) and per-candidate bests vs the oracle"""
+    fam = synth.make_family(7, 40, 150, 0.15, one_sided_frac=0.2)
+    osc = oracle.scoring("14p43g")
+    p = make_params(bandwidth=40, minimprovement=30, L=120, when_to_stop=1000)
+    lib = ramcu.upload_library(fam.sequence)
+    try:
+        for d in (1, 0):
+            want = oracle.extend(d, fam.cores, fam.sequence, osc, p, trace=True)
+            rows, best, sums = ramcu.debug_rows(lib, d, fam.cores, osc.to_product(), p, 120)
+            assert np.array_equal(sums, want["trace"][:, :4])
+    finally:
+        ramcu.free_library(lib)
+
+
+def test_edge_cases(ramcu, oracle):
+    osc = oracle.scoring("20p43g")
+    sc = osc.to_product()
+    fam = synth.make_family(8, 12, 60, 0.1)
+    lib = ramcu.upload_library(fam.sequence)
+    try:
+        # nothing extendable in one direction
+        cores = fam.cores.copy()
+        cores["right_extendable"] = 0
+        p = make_params(bandwidth=14, L=500)
+        for d in (1, 0):
+            want = oracle.extend(d, cores, fam.sequence, osc, p)
+            got = _got(*ramcu.extend(lib, d, cores, sc, p))
+            support.compare_extend(want, got, f"no-right dir={d}")
+        # empty family, L = 0, L = 1, when_to_stop = 0/1, a single instance
+        for cs, kw in ((fam.cores[:0], dict(L=300)), (fam.cores, dict(L=0)), (fam.cores, dict(L=1)),
+                       (fam.cores, dict(L=300, when_to_stop=0)), (fam.cores, dict(L=300, when_to_stop=1)),
+                       (fam.cores[:1], dict(L=300)), (fam.cores, dict(L=300, minimprovement=0)),
+                       (fam.cores, dict(L=300, cappenalty=0))):
+            p = make_params(bandwidth=14, **kw)
+            for d in (1, 0):
+                want = oracle.extend(d, cs, fam.sequence, osc, p)
+                got = _got(*ramcu.extend(lib, d, cs, sc, p))
+                support.compare_extend(want, got, f"edge {kw} n={cs.size} dir={d}")
+        with pytest.raises(RamCuError):
+            ramcu.extend(lib, 1, fam.cores, sc, make_params(bandwidth=600))
+    finally:
+        ramcu.free_library(lib)
+
+
+def test_batch_equals_individual_runs(ramcu, oracle):
+    """many families in one launch (ramcu_batch_run) == each family on its own == oracle"""
+    specs = synth.config5_specs(5, 12)
+    fams = []
+    for s in specs:
+        s = dict(s, n=max(20, s["n"] // 40), flank=max(60, s["flank"] // 12))
+        fams.append(synth.family_from_spec(s))
+    res = batch.extend_families(ramcu, fams)
+    for f, r in zip(fams, res):
+        osc = oracle.scoring(f.params["matrix"])
+        p = make_params(**{k: v for k, v in f.params.items() if k != "matrix"})
+        for d, got in ((1, r.right), (0, r.left)):
+            want = oracle.extend(d, f.cores, f.sequence, osc, p)
+            support.compare_extend(want, got, f"batch dir={d}")
+
+
+def test_full_size_properties(ramcu):
+    """BASELINE config 4 scale (10k instances is too slow for the oracle): independent band
+    tilings must agree bit for bit, instance order must not matter, and mirroring the library
+    (reverse-complement sequence[], flip every strand) must leave both extensions unchanged."""
+    fam = synth.make_family(4, 10000, 1200, 0.15)
+    sc = ramcu.scoring("14p43g")
+    lib = ramcu.upload_library(fam.sequence)
+    outs = {}
+    try:
+        for G in (1, 2, 4):
+            p = make_params(bandwidth=40, minimprovement=30, L=20000, lanes_per_instance=G)
+            outs[G] = [_got(*ramcu.extend(lib, d, fam.cores, sc, p)) for d in (1, 0)]
+        for G in (2, 4):
+            for a, b in zip(outs[1], outs[G]):
+                support.compare_extend(a, b, f"G=1 vs G={G}")
+        assert outs[1][0]["extended_bp"] > 1000 and outs[1][1]["extended_bp"] > 1000
+        # permutation invariance
+        perm = np.random.default_rng(0).permutation(fam.cores.size)
+        p = make_params(bandwidth=40, minimprovement=30, L=20000)
+        for d in (1, 0):
+            got = _got(*ramcu.extend(lib, d, fam.cores[perm], sc, p))
+            assert got["extended_bp"] == outs[1][1 - d]["extended_bp"]
+            assert np.array_equal(got["master"], outs[1][1 - d]["master"])
+            assert np.array_equal(got["ext_len"], outs[1][1 - d]["ext_len"][perm])
+            assert np.array_equal(got["score_add"], outs[1][1 - d]["score_add"][perm])
+    finally:
+        ramcu.free_library(lib)
+    # mirror: reverse-complement sequence[] (position p -> n-1-p) and flip every strand; the
+    # consensus orientation of each core is unchanged, so both extensions must be identical
+    n = fam.sequence.size
+    mseq = synth.revcomp(fam.sequence)
+    mc = fam.cores.copy()
+    mc["left_seq_pos"] = n - 1 - fam.cores["left_seq_pos"]
+    mc["right_seq_pos"] = n - 1 - fam.cores["right_seq_pos"]
+    mc["lower_seq_bound"] = n - 1 - fam.cores["upper_seq_bound"]
+    mc["upper_seq_bound"] = n - 1 - fam.cores["lower_seq_bound"]
+    mc["orient"] = 1 - fam.cores["orient"]
+    lib = ramcu.upload_library(mseq)
+    try:
+        p = make_params(bandwidth=40, minimprovement=30, L=20000)
+        for d in (1, 0):
+            got = _got(*ramcu.extend(lib, d, mc, sc, p))
+            support.compare_extend(outs[1][1 - d], got, f"mirror dir={d}")
+    finally:
+        ramcu.free_library(lib)
+
+
+@pytest.mark.parametrize("name", gio.cli_case_names())
+def test_cli_outputs_byte_identical(name, tmp_path):
+    """the product CLI (reference main() + CUDA extend_alignment) writes byte-identical -cons,
+    -outtsv, -outfa and stdout to the reference RAMExtend (golden outputs)"""
+    exe = os.path.join(ROOT, "repeatafterme_b200", "bin", "RAMExtend")
+    if not os.path.exists(exe):
+        pytest.skip("bin/RAMExtend not built (needs the reference's host objects)")
+    from tests.cases import filter_stdout
+    case = gio.load_cli(name)
+    tb, rg = str(tmp_path / "in.2bit"), str(tmp_path / "in.tsv")
+    synth.write_twobit(tb, case["names"], case["seqs"])
+    synth.write_ranges(rg, case["bed"])
+    cmd = [exe, "-twobit", tb, "-ranges", rg, "-outtsv", str(tmp_path / "out.tsv"), "-outfa",
+           str(tmp_path / "out.fa"), "-cons", str(tmp_path / "cons.fa")] + case["flags"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert filter_stdout(r.stdout, str(tmp_path)) == case["want"]["stdout.txt"]
+    for f in ("out.tsv", "out.fa", "cons.fa"):
+        p = tmp_path / f
+        assert (p.read_text() if p.exists() else "") == case["want"][f], f

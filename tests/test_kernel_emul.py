@@ -1,0 +1,82 @@
+"""The real kernel source (csrc/extend_kernel.cuh) + the real host flatten logic (csrc/flatten.h)
+compiled for the CPU against a lock-step SIMT emulation (tests/emul), diffed against the oracle.
+This is a logic check that runs without a GPU; the GPU parity tests are tests/test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from repeatafterme_b200 import synth
+from repeatafterme_b200.abi import CORE_DTYPE, make_params
+from tests import golden_io as gio
+from tests import support
+
+
+@pytest.mark.parametrize("cfg,threads", [
+    ((11, 1, 11), 32), ((6, 2, 11), 32), ((3, 4, 11), 64), ((4, 4, 0), 32), ((16, 32, 0), 64),
+])
+def test_emul_b5_family(emul, oracle, cfg, threads):
+    fam = synth.make_family(3, 14, 70, 0.15, pad=0, one_sided_frac=0.3, n_frac=0.02)
+    osc = oracle.scoring("18p43g")
+    p = make_params(bandwidth=5, minimprovement=27, L=400, when_to_stop=25)
+    for d in (1, 0):
+        want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+        got = emul.extend(cfg, d, fam.cores, fam.sequence, osc.to_product(), p, threads=threads)
+        support.compare_extend(want, got, f"cfg={cfg} dir={d}")
+
+
+@pytest.mark.parametrize("cfg,B,matrix", [
+    ((8, 4, 29), 14, "20p43g"), ((29, 1, 29), 14, "20p43g"), ((21, 4, 81), 40, "14p43g"),
+    ((11, 8, 81), 40, "14p43g"), ((32, 4, 0), 40, "14p43g"),
+])
+def test_emul_multi_cta_ragged(emul, oracle, cfg, B, matrix):
+    """several CTAs per family (grid exchange), instances that run out of flank at different
+    rows (per-cell bounds path, retired warps)"""
+    from tests.cases import ragged_family
+    fam = ragged_family(5, 20, 90)
+    osc = oracle.scoring(matrix)
+    p = make_params(bandwidth=B, minimprovement=27, L=300, when_to_stop=20)
+    for d in (1, 0):
+        want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+        got = emul.extend(cfg, d, fam.cores, fam.sequence, osc.to_product(), p, threads=32)
+        support.compare_extend(want, got, f"cfg={cfg} dir={d}")
+
+
+@pytest.mark.parametrize("cfg", [(11, 1, 11), (3, 4, 11), (4, 4, 0)])
+def test_emul_unit_vectors_forced_consensus(emul, cfg):
+    """bnw_extend.c:1384-1651 through the kernel: forced consensus, every committed band row"""
+    u = gio.load_unit()
+    B = u["bandwidth"]
+    from tests.support import Oracle
+    sc = Oracle().scoring(u["matrix"]).to_product()
+    for side, direction in (("left", 0), ("right", 1)):
+        seq = np.array(u[f"p_{side}"], dtype=np.uint8)
+        cores = np.zeros(3, dtype=CORE_DTYPE)
+        for n in range(3):
+            l, r, lo, hi, orient = u[f"{side}_cores"][n]
+            cores[n]["left_seq_pos"], cores[n]["right_seq_pos"] = l, r
+            cores[n]["lower_seq_bound"], cores[n]["upper_seq_bound"], cores[n]["orient"] = lo, hi, orient
+            cores[n]["left_extendable"] = cores[n]["right_extendable"] = 1
+        nrows = len(u["cons_base"])
+        p = make_params(bandwidth=B, L=nrows)
+        got = emul.extend(cfg, direction, cores, seq, sc, p, threads=32, dbg_rows=nrows,
+                          forced=u["cons_base"])
+        for n in range(3):
+            for row in range(nrows):
+                want = u["reference_rows"][side][n][row]
+                assert got["rows"][row, n, :, 0].tolist() == want["sub"], (side, n, row)
+                assert got["rows"][row, n, :, 1].tolist() == want["gap"], (side, n, row)
+                assert got["best"][row, n, u["cons_base"][row]] == want["best"]
+        if side == "right":
+            assert got["rows"][6, 0, :, 1].tolist() == u["final_right_gap"]
+            assert got["rows"][6, 0, :, 0].tolist() == u["final_right_sub"]
+
+
+@pytest.mark.parametrize("name,cfg", [("config1_default", (8, 4, 29)), ("l_limited", (4, 4, 0)),
+                                      ("identical", (15, 2, 29))])
+def test_emul_golden(emul, oracle, name, cfg):
+    case = gio.load_flat(name)
+    sc = gio.oracle_scoring_for(case, oracle).to_product()
+    p = gio.params_for(case)
+    for d in (1, 0):
+        got = emul.extend(cfg, d, case["cores"], case["sequence"], sc, p, threads=64)
+        gio.check_against_golden(case, d, got, f"{name} dir={d}")
