@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- banded-DP extension throughput (GCUPS) of the CUDA path, with the reference's own
+CPU implementation timed beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [--steps K] [--warmup W]      # reference RAMExtend on host cores
+
+Workload (BASELINE.json configs[3], SURVEY.md 8d "config 4"): one synthetic family of 10 000
+instances at ~15 % divergence with 5 kb flanks, bandwidth 40, matrix 14p43g, minimprovement 30,
+L 20000. One STEP = one full extension of the family = the two extend_alignment() calls the
+reference's main() makes (right pass, then left pass), ~3.3e10 cell updates. With N GPUs every
+rank extends its own family of that shape (families are independent: no collective on the data
+path, weak scaling); `value` = cell updates of all ranks / max-over-ranks device time.
+
+CU (cell update) = one band cell x one instance x one row x one candidate base:
+    CU = sum_dir rows_processed * n_extendable * (2*bandwidth+1) * 4          
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n=10000, flank=5000, divergence=0.15, bandwidth=40, matrix="14p43g", minimprovement=30,
+                cappenalty=-90, L=20000, when_to_stop=100)
+OPS_PER_CU = 8            # algorithmic int32 add/max per cell update
+NOMINAL_INT32_GOPS = 148 * 64 * 1.965   # 148 SM x 64 INT32 lanes x 1.965 GHz
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own extend_alignment() object code (oracle/_ref/libramref.so)
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, n, flank, kind = args
+    from repeatafterme_b200 import synth
+    from repeatafterme_b200.abi import make_params
+    from tests import support
+    fam = synth.make_family(seed, n, flank, WORKLOAD["divergence"])
+    p = make_params(bandwidth=WORKLOAD["bandwidth"], minimprovement=WORKLOAD["minimprovement"],
+                    cappenalty=WORKLOAD["cappenalty"], L=WORKLOAD["L"], when_to_stop=WORKLOAD["when_to_stop"])
+    ora = support.Oracle()
+    sc = ora.scoring(WORKLOAD["matrix"])
+    ref = support.Reference.try_load() if kind == "reference" else None
+    secs, cu = 0.0, 0.0
+    for d in (1, 0):
+        if ref is not None:
+            o = ref.extend(d, fam.cores, fam.sequence, sc, p)
+            secs += o["seconds"]
+            rows = o["rows_processed"]
+        else:
+            t0 = time.perf_counter()
+            o = ora.extend(d, fam.cores, fam.sequence, sc, p)
+            secs += time.perf_counter() - t0
+            rows = o["rows_processed"]
+        next_ = int(((fam.cores["right_extendable"] if d else fam.cores["left_extendable"]) != 0).sum())
+        cu += rows * next_ * (2 * WORKLOAD["bandwidth"] + 1) * 4.0
+    return secs, cu
+
+
+def cpu_baseline(n_inst: int, flank: int, procs: int, seed0: int = 900):
+    """one sample family per process on `procs` host cores at once (the reference is single
+    threaded; util/extend-stk.pl runs one RAMExtend process per family). Returns
+    (aggregate GCUPS, single-process GCUPS, kind)."""
+    import multiprocessing as mp
+    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libramref.so")) else "port"
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        outs = pool.map(_cpu_worker, [(seed0 + i, n_inst, flank, kind) for i in range(procs)])
+    wall = time.perf_counter() - t0
+    cu = sum(o[1] for o in outs)
+    slowest = max(o[0] for o in outs)
+    single = outs[0][1] / outs[0][0] / 1e9
+    return cu / slowest / 1e9, single, kind, wall
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_inst, flank = 32, WORKLOAD["flank"]
+    vals = []
+    for step in range(args.warmup + args.steps):
+        agg, single, kind, wall = cpu_baseline(n_inst, flank, cores, seed0=900 + 1000 * step)
+        if step >= args.warmup:
+            vals.append((agg, single, wall))
+    agg = float(np.mean([v[0] for v in vals]))
+    single = float(np.mean([v[1] for v in vals]))
+    sample = (f"{cores} processes, each the two extend_alignment() calls of one synthetic family of "
+              f"{n_inst} instances x {flank} bp flanks (config-4 shape, DP time only via clock_gettime)")
+    line = {"impl": "reference", "metric": "banded_dp_gcups", "value": round(agg, 4), "unit": "GCUPS",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1e3 * float(np.mean([v[2] for v in vals])), 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": round(agg, 4), "unit": "GCUPS", "cores": cores, "kind": kind,
+                             "sample": sample, "single_process_value": round(single, 4)},
+            "e2e": {"value": round(agg, 4), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "synthetic single family per GPU: 10k instances, ~15% divergence, 5 kb flanks, "
+                        "bandwidth 40, 14p43g, minimprovement 30, L 20000 (BASELINE configs[3])",
+            "instances": WORKLOAD["n"], "flank_bp": WORKLOAD["flank"], "bandwidth": WORKLOAD["bandwidth"],
+            "matrix": WORKLOAD["matrix"], "families_per_step": n_gpus, "parallelism": f"families x{n_gpus}",
+            "l2": "L2 flushed between timed steps (256 MiB write)"}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from repeatafterme_b200 import RamCu, batch, synth
+    from repeatafterme_b200.abi import make_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rc = RamCu(local)
+    stream = torch.cuda.Stream()          # a real (non-default) stream, shared with the C-ABI
+    torch.cuda.set_stream(stream)
+    rc.set_stream(stream.cuda_stream)
+
+    n, flank = args.instances, args.flank
+    t0 = time.time()
+    fam = synth.make_family(4 + 17 * rank, n, flank, WORKLOAD["divergence"])
+    log(f"[rank {rank}] generated family N={n} flank={flank} ({fam.sequence.size / 1e6:.1f} Mbases) in {time.time() - t0:.1f}s")
+    sc = rc.scoring(WORKLOAD["matrix"])
+    p = make_params(bandwidth=WORKLOAD["bandwidth"], minimprovement=WORKLOAD["minimprovement"],
+                    cappenalty=WORKLOAD["cappenalty"], L=WORKLOAD["L"], when_to_stop=WORKLOAD["when_to_stop"],
+                    lanes_per_instance=args.lanes)
+
+    # ---- device-resident leg: library + descriptors in HBM before the timed region -------------
+    host_seq = torch.from_numpy(fam.sequence).pin_memory()
+    lib = rc.upload_library(host_seq.numpy())
+    jobs = [rc.job_create(lib, d, fam.cores, sc, p) for d in (1, 0)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step_device():
+        for j in jobs:
+            rc.job_run(j)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()                       # evict the library / state from L2 between steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_device()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop()
+    outs = [rc.job_fetch(j, fam.cores.size, p.L) for j in jobs]
+    cu_step = sum(o[0].rows_processed * o[0].n_extendable * (2 * p.bandwidth + 1) * 4.0 for o in outs)
+    lanes = outs[0][0].lanes_per_instance
+    bp = (outs[0][0].extended_bp, outs[1][0].extended_bp)
+
+    # ---- end-to-end leg: host buffers in, host results out, every step ---------------------------
+    def step_e2e(verbose=False):
+        t = [time.perf_counter()]
+        h = rc.upload_library(host_seq.numpy())
+        t.append(time.perf_counter())
+        res = []
+        for d in (1, 0):
+            res.append(rc.extend(h, d, fam.cores, sc, p))
+            t.append(time.perf_counter())
+        rc.free_library(h)
+        t.append(time.perf_counter())
+        if verbose:
+            log("[e2e breakdown ms] upload %.1f right %.1f left %.1f free %.1f" %
+                tuple(1e3 * (b - a) for a, b in zip(t[:-1], t[1:])))
+        return res
+
+    step_e2e(verbose=True)
+    step_e2e(verbose=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = int(fam.sequence.nbytes + 2 * fam.cores.nbytes)
+    d2h = int(sum(x[1].nbytes + x[2].nbytes + x[3].nbytes + 32 for x in r))
+
+    peak_gops = rc.int32_peak_gops()
+
+    # ---- config-5 style batch: many independent families sharing the GPU (families/s) -------------
+    fam_info = None
+    if args.families > 0 and world == 1:
+        specs = synth.config5_specs(5, 2000)
+        pick = np.random.default_rng(0).choice(len(specs), size=args.families, replace=False)
+        fams5 = [synth.family_from_spec(specs[i]) for i in sorted(pick)]
+        batch.extend_families(rc, fams5[:2])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res5 = batch.extend_families(rc, fams5)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        cu5 = sum(x.cell_updates for x in res5)
+        fam_info = {"n_families": len(fams5), "instances": int(sum(f.n for f in fams5)),
+                    "families_per_s": round(len(fams5) / dt, 2), "gcups_e2e": round(cu5 / dt / 1e9, 1),
+                    "seconds": round(dt, 3),
+                    "what": "seeded sample of the BASELINE configs[4] family mix (N 100-10k log-uniform, "
+                            "bandwidth 20-100, flank 0.5-5 kb), host buffers in / host results out"}
+
+    for j in jobs:
+        rc.job_free(j)
+    rc.free_library(lib)
+
+    # ---- max over ranks -------------------------------------------------------------------------
+    stats = torch.tensor([dev_ms, e2e_s, cu_step], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s, cu_total = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        cu_total = cu_step
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    gcups = cu_total * args.steps / (dev_ms * 1e-3) / 1e9
+    e2e_gcups = cu_total * args.steps / e2e_s / 1e9
+    per_gpu_gops = cu_step * args.steps / (dev_ms * 1e-3) / 1e9 * OPS_PER_CU
+    flank_bytes = sum(o[0].rows_processed * o[0].n_extendable for o in outs) / 4.0   # 2 bits/base/row
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    cpu = None
+    if world == 1 or rank == 0:
+        cores = os.cpu_count() or 1
+        agg, single, kind, wall = cpu_baseline(args.cpu_instances, WORKLOAD["flank"], cores)
+        cpu = {"value": round(agg, 4), "unit": "GCUPS", "cores": cores, "kind": kind,
+               "single_process_value": round(single, 4),
+               "sample": f"{cores} processes at once, each one synthetic family of {args.cpu_instances} instances x "
+                         f"{WORKLOAD['flank']} bp flanks (config-4 shape), reference extend_alignment() object "
+                         f"code timed with clock_gettime around the two calls ({wall:.1f}s wall)"}
+
+    line = {"metric": "banded_dp_gcups", "value": round(gcups, 1), "unit": "GCUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": dict(workload_config(world), instances=n, flank_bp=flank,
+                                                lanes_per_instance=lanes, extended_bp=list(bp)),
+            "families_per_s": round(world * args.steps / (dev_ms * 1e-3), 2),
+            "roofline": {"bound": "int32_alu", "achieved": round(per_gpu_gops, 1), "peak": round(peak_gops, 1),
+                         "unit": "Gop/s", "frac": round(per_gpu_gops / peak_gops, 4),
+                         "peak_source": "measured in this run (ramcu_int32_peak: independent fused add+max chains "
+                                        "on all SMs, one op per instruction-lane)",
+                         "nominal_peak": round(NOMINAL_INT32_GOPS, 1),
+                         "frac_of_nominal": round(per_gpu_gops / NOMINAL_INT32_GOPS, 4),
+                         "ops_per_cell_update": OPS_PER_CU, "traffic": None,
+                         "hbm": {"achieved": round(flank_bytes * args.steps / (dev_ms * 1e-3) / 1e9, 3),
+                                 "peak": hbm_peak, "unit": "GB/s",
+                                 "note": "algorithmic flank bytes (2 bits per base per instance-row); the path is "
+                                         "ALU bound, HBM is a sanity figure"}},
+            "cpu_baseline": cpu,
+            "e2e": {"value": round(e2e_gcups, 1), "unit": "GCUPS", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": round(1e3 * e2e_s / args.steps, 2),
+                    "what": "ramcu_library_upload (pinned host bytes -> HBM, packed on device) + two ramcu_extend "
+                            "calls with host outputs, per step"},
+            "gpu_launches": 2 * args.steps,
+            "clocks": clocks}
+    if fam_info:
+        line["family_batch"] = fam_info
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--instances", type=int, default=WORKLOAD["n"])
+    ap.add_argument("--flank", type=int, default=WORKLOAD["flank"])
+    ap.add_argument("--lanes", type=int, default=0, help="force lanes per instance (0 = auto)")
+    ap.add_argument("--families", type=int, default=12, help="size of the config-5 family-batch sample (0 = skip)")
+    ap.add_argument("--cpu-instances", type=int, default=48, help="instances of the CPU-baseline sample family")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

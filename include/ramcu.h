@@ -108,6 +108,10 @@ void ramcu_destroy(ramcu_ctx *ctx);
 int ramcu_set_stream(ramcu_ctx *ctx, void *cuda_stream);
 int ramcu_device_info(ramcu_ctx *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
 
+/* Measurement aid: INT32 ALU peak of the device in giga instruction-lanes per second (independent
+ * fused add+max chains on every SM) -- the roofline denominator bench.py reports against. */
+int ramcu_int32_peak(ramcu_ctx *ctx, double *gops_per_s, double *elapsed_ms);
+
 /* Built-in scoring systems of score_system.c (getMatrix / getRepeatScoutMatrix). */
 int ramcu_scoring_by_name(const char *name, int rs_match, int rs_mismatch, int rs_gap,
                           ramcu_scoring_t *out);

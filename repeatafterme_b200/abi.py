@@ -33,7 +33,7 @@ NCODES = 5  # A,C,G,T,N
 #: every symbol include/ramcu.h declares
 ABI_SYMBOLS = (
     "ramcu_last_error", "ramcu_abi_version", "ramcu_init", "ramcu_destroy", "ramcu_set_stream",
-    "ramcu_device_info", "ramcu_scoring_by_name", "ramcu_library_upload",
+    "ramcu_device_info", "ramcu_int32_peak", "ramcu_scoring_by_name", "ramcu_library_upload",
     "ramcu_library_from_device", "ramcu_library_free", "ramcu_extend", "ramcu_job_create",
     "ramcu_job_run", "ramcu_job_fetch", "ramcu_job_free", "ramcu_batch_run", "ramcu_debug_rows",
 )
@@ -123,6 +123,7 @@ def load_ramcu(path: str = LIB_PATH) -> C.CDLL:
     lib.ramcu_set_stream.argtypes = [vp, vp]
     lib.ramcu_device_info.argtypes = [vp, P(i32), P(i32), P(i32)]
     lib.ramcu_scoring_by_name.argtypes = [C.c_char_p, i32, i32, i32, P(Scoring)]
+    lib.ramcu_int32_peak.argtypes = [vp, P(C.c_double), P(C.c_double)]
     lib.ramcu_library_upload.argtypes = [vp, vp, u64, P(vp)]
     lib.ramcu_library_from_device.argtypes = [vp, vp, u64, P(vp)]
     lib.ramcu_library_free.argtypes = [vp, vp]
@@ -179,6 +180,11 @@ class RamCu:
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         self._check(self.lib.ramcu_device_info(self.ctx, C.byref(a), C.byref(b), C.byref(c)))
         return {"sm_count": a.value, "cc": (b.value, c.value)}
+
+    def int32_peak_gops(self) -> float:
+        g, ms = C.c_double(), C.c_double()
+        self._check(self.lib.ramcu_int32_peak(self.ctx, C.byref(g), C.byref(ms)))
+        return g.value
 
     def set_stream(self, cuda_stream: int | None):
         self._check(self.lib.ramcu_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)))

@@ -672,4 +672,30 @@ pack_library_kernel(const uint8_t *__restrict__ bytes, const unsigned long long 
   }
 }
 
+
+// INT32 ALU roofline denominator: kChains independent max-plus chains per thread, one fused
+// add+max (VIADDMNMX) per chain per step, on every SM. Counted as ONE op per instruction-lane.
+constexpr int kPeakChains = 16;
+__global__ void __launch_bounds__(256)
+int32_peak_kernel(int *__restrict__ out, const int iters, const int seed)
+{
+  int x[kPeakChains];
+#pragma unroll
+  for (int k = 0; k < kPeakChains; ++k)
+    x[k] = seed + k * 7 + (int) threadIdx.x;
+  const int inc = seed | 1, floor_ = -seed;
+  for (int i = 0; i < iters; ++i)
+  {
+#pragma unroll
+    for (int k = 0; k < kPeakChains; ++k)
+      x[k] = max(x[k] + inc, floor_ + k);
+  }
+  int acc = 0;
+#pragma unroll
+  for (int k = 0; k < kPeakChains; ++k)
+    acc ^= x[k];
+  if (acc == 0x7fffffff)
+    out[0] = acc;
+}
+
 }  // namespace ramcu

@@ -257,6 +257,31 @@ extern "C" int ramcu_scoring_by_name(const char *name, int rs_match, int rs_mism
   return fail(RAMCU_ERR_ARG, "Matrix name not found: %s", name);
 }
 
+// Measured INT32 ALU peak (instruction-lanes per second) of this device: the roofline denominator
+// of the extension kernel. Runs ~iters*16 fused add+max ops per thread on a grid
+// that fills every SM.
+extern "C" int ramcu_int32_peak(ramcu_ctx *c, double *gops, double *ms_out)
+{
+  if (!c || !gops)
+    return fail(RAMCU_ERR_ARG, "ramcu_int32_peak: NULL argument");
+  CK(cudaSetDevice(c->device));
+  int *d = nullptr;
+  CK(cudaMalloc(&d, sizeof(int)));
+  const int iters = 20000, grid = c->sm_count * 8, block = 256;
+  int32_peak_kernel<<<grid, block, 0, c->stream>>>(d, 100, 3);   // warm-up
+  CK(cudaEventRecord(c->ev0, c->stream));
+  int32_peak_kernel<<<grid, block, 0, c->stream>>>(d, iters, 3);
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  cudaFree(d);
+  *gops = (double) grid * block * (double) iters * kPeakChains / (ms * 1e-3) / 1e9;
+  if (ms_out)
+    *ms_out = ms;
+  return RAMCU_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // library
 // ------------------------------------------------------------------------------------------

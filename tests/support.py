@@ -154,8 +154,9 @@ class Reference:
                                     m.ctypes.data, sc.gapopen, sc.gapextn, p.bandwidth, p.cappenalty,
                                     p.minimprovement, p.L, p.when_to_stop, verbose, master.ctypes.data,
                                     ext_len.ctypes.data, score_add.ctypes.data, C.byref(secs))
-        return dict(extended_bp=bp, master=master, ext_len=ext_len, score_add=score_add,
-                    seconds=secs.value)
+        rows = int((master != 100).sum())   # the shim pre-fills master[] with 100
+        return dict(extended_bp=bp, rows_processed=rows, master=master, ext_len=ext_len,
+                    score_add=score_add, seconds=secs.value)
 
     def load(self, twobit, ranges, max_flanking_bp):
         n, slen = i32(), u64()
