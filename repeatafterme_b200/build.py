@@ -25,17 +25,43 @@ def _newer(target, sources):
     return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
 
 
-def build_libramcu(force=False, verbose=False):
-    out = os.path.join(CSRC, "libramcu.so")
-    srcs = [os.path.join(CSRC, f) for f in ("ramcu.cu", "extend_kernel.cuh", "flatten.h")]
-    srcs.append(os.path.join(ROOT, "include", "ramcu.h"))
-    if not force and not _newer(out, srcs):
-        return out
-    cmd = [NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
-           "-o", out, os.path.join(CSRC, "ramcu.cu")]
+KERNEL_UNITS = ["kernels_b14", "kernels_b20", "kernels_b40", "kernels_b60", "kernels_b80", "kernels_b100",
+                "kernels_generic"]
+
+
+def _nvcc_obj(unit, verbose=False):
+    src, obj = os.path.join(CSRC, unit + ".cu"), os.path.join(CSRC, unit + ".o")
+    cmd = [NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
-    subprocess.check_call(cmd, cwd=CSRC)
+    log = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if log.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {unit}:\n{log.stdout}\n{log.stderr}")
+    return obj, log.stderr
+
+
+def build_libramcu(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo, one object per translation unit
+    (compiled in parallel), linked into csrc/libramcu.so."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    out = os.path.join(CSRC, "libramcu.so")
+    common = [os.path.join(CSRC, f) for f in ("extend_kernel.cuh", "aux_kernels.cuh", "flatten.h", "kernels.h")]
+    common.append(os.path.join(ROOT, "include", "ramcu.h"))
+    units = ["ramcu"] + KERNEL_UNITS
+    todo = [u for u in units
+            if force or _newer(os.path.join(CSRC, u + ".o"), [os.path.join(CSRC, u + ".cu")] + common)]
+    logs = {}
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1)) as ex:
+            for u, (obj, err) in zip(todo, ex.map(lambda u: _nvcc_obj(u, verbose), todo)):
+                logs[u] = err
+    objs = [os.path.join(CSRC, u + ".o") for u in units]
+    if todo or not os.path.exists(out):
+        subprocess.check_call([NVCC, *ARCH, "--shared", "-o", out, *objs], cwd=CSRC)
+    if verbose:
+        for u, err in logs.items():
+            print(err)
     return out
 
 

@@ -59,11 +59,12 @@ struct FamDev
   int *thigh;             // out: trimmed_sequence_high_score      (per extendable instance)
   int *tpos;              // out: trimmed_sequence_high_score_pos
   int *result;            // out: [0] max_row [1] rows_processed [2] stop_row [3] max_ext
-  unsigned long long *slots;    // [L][4] per-column (count << 48 | sum) accumulators, zeroed
+  unsigned long long *slots;    // [2][n_ctas][4] (tag << 32 | sum) column exchange, zeroed
   const unsigned char *forced;  // debug: forced consensus per row (or NULL)
   int *dbg_rows;          // debug: [rows][n_ext][W][2]
   int *dbg_best;          // debug: [rows][n_ext][4]
   int *dbg_sums;          // debug: [rows][4]
+  long long *dbg_wait;    // diagnostics: per CTA [0] cycles spent in the grid exchange [1] total cycles
   int n_ext, n_ctas, cta0, B;
   int W, go, ge, cap;
   int minimp, L, stop, pad;
@@ -77,6 +78,35 @@ __device__ __forceinline__ int sel4(int a, int x0, int x1, int x2, int x3)
   const int lo = (a & 1) ? x1 : x0;
   const int hi = (a & 1) ? x3 : x2;
   return (a & 2) ? hi : lo;
+}
+
+// max / min over the G lanes of an instance, result in every lane of the group. Powers of two use
+// an xor butterfly; other group sizes an upward inclusive scan + broadcast from the last lane.
+template <int G>
+__device__ __forceinline__ int group_max(int v, const int gl, const int lane)
+{
+  if (G == 1)
+    return v;
+  if ((G & (G - 1)) == 0)
+  {
+#pragma unroll
+    for (int d = G >> 1; d >= 1; d >>= 1)
+      v = max(v, __shfl_xor_sync(kFull, v, d));
+    return v;
+  }
+#pragma unroll
+  for (int d = 1; d < G; d <<= 1)
+  {
+    const int t = __shfl_up_sync(kFull, v, d);
+    if (gl >= d)
+      v = max(v, t);
+  }
+  return __shfl_sync(kFull, v, min(lane - gl + G - 1, 31));
+}
+template <int G>
+__device__ __forceinline__ int group_min(int v, const int gl, const int lane)
+{
+  return -group_max<G>(-v, gl, lane);
 }
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
@@ -226,31 +256,77 @@ __device__ __forceinline__ void band_pass(int (&Sp)[C], int (&Gp)[C], const int 
     gout[a] = gprev[a];
 }
 
-// Grid-level reduction of the four per-candidate partial sums of column r between the CTAs of a
-// family. Column r owns four 64-bit accumulators (zeroed before the launch); every CTA adds
-// (1 << 48 | partial) with one RED per candidate, so the arrival count travels in the same word
-// as the data: a reader that sees count == n_ctas has the complete sum in the low 32 bits
-// (mod 2^32, exactly the reference's int arithmetic). One L2 round trip, no fence, no reset, and
-// only warp 0 of each CTA spends issue slots on it.
-__device__ __forceinline__ void grid_exchange(unsigned long long *acc_row, const int n_ctas,
-                                              unsigned (&sums)[4], const int lane)
+// Grid-level exchange of the four per-candidate column sums between the CTAs of a family.
+// Every CTA publishes its four sums as (tag << 32 | sum) 64-bit words in its own 32-byte slot
+// (plain stores: no atomics, no serialisation point in L2); warp 0 of every CTA then gathers all
+// slots, kGatherU independent 32-byte loads per lane in flight, and re-reads only the slots whose
+// tag (column + 1) has not arrived yet. The tag travels in the same word as the data, so no fence
+// is needed and one L2 round trip suffices once the last CTA has published. Slots are double
+// buffered by column parity: a CTA overwrites a slot two columns later, after everyone read it.
+constexpr int kGatherU = 5;
+
+__device__ __forceinline__ void ld_slot(const unsigned long long *p, unsigned long long (&w)[4])
 {
-  unsigned lo = 0;
+#ifdef RAMCU_EMUL
+  for (int i = 0; i < 4; ++i)
+    w[i] = emul_ld_relaxed_u64(p + i);
+#else
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
+               : "=l"(w[0]), "=l"(w[1]) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
+               : "=l"(w[2]), "=l"(w[3]) : "l"(p + 2) : "memory");
+#endif
+}
+
+__device__ __forceinline__ void grid_exchange(unsigned long long *slots, const int n_ctas,
+                                              const int cta_in_fam, const int par,
+                                              const unsigned tag, unsigned (&sums)[4],
+                                              const int lane)
+{
+  unsigned long long *base = slots + (size_t) par * n_ctas * 4;
   if (lane < 4)
   {
     const unsigned mine = (unsigned) sel4(lane, (int) sums[0], (int) sums[1], (int) sums[2], (int) sums[3]);
-    atomicAdd(acc_row + lane, (1ull << 48) | (unsigned long long) mine);
-    unsigned long long v;
+    st_relaxed_u64(base + (size_t) cta_in_fam * 4 + lane, ((unsigned long long) tag << 32) | mine);
+  }
+  unsigned acc[4] = {0, 0, 0, 0};
+  for (int b0 = 0; b0 < n_ctas; b0 += 32 * kGatherU)
+  {
+    unsigned long long w[kGatherU][4];
+    bool done[kGatherU];
+#pragma unroll
+    for (int u = 0; u < kGatherU; ++u)
+      done[u] = (b0 + u * 32 + lane) >= n_ctas;
+    bool all;
     do
     {
-      v = ld_relaxed_u64(acc_row + lane);
-    } while ((int) (v >> 48) != n_ctas);
-    lo = (unsigned) v;
+#pragma unroll
+      for (int u = 0; u < kGatherU; ++u)
+        if (!done[u])
+          ld_slot(base + (size_t) (b0 + u * 32 + lane) * 4, w[u]);
+      all = true;
+#pragma unroll
+      for (int u = 0; u < kGatherU; ++u)
+        if (!done[u])
+        {
+          const bool ok = ((unsigned) (w[u][0] >> 32) == tag) && ((unsigned) (w[u][1] >> 32) == tag) &&
+                          ((unsigned) (w[u][2] >> 32) == tag) && ((unsigned) (w[u][3] >> 32) == tag);
+          if (ok)
+          {
+            done[u] = true;
+            acc[0] += (unsigned) w[u][0];
+            acc[1] += (unsigned) w[u][1];
+            acc[2] += (unsigned) w[u][2];
+            acc[3] += (unsigned) w[u][3];
+          }
+          else
+            all = false;
+        }
+    } while (!all);
   }
-  sums[0] = __shfl_sync(kFull, lo, 0);
-  sums[1] = __shfl_sync(kFull, lo, 1);
-  sums[2] = __shfl_sync(kFull, lo, 2);
-  sums[3] = __shfl_sync(kFull, lo, 3);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    sums[a] = (unsigned) __reduce_add_sync(kFull, (int) acc[a]);
 }
 
 // per-CTA shared state: score LUT, per-warp partial column sums, broadcast sums, logical CTA id
@@ -266,7 +342,8 @@ template <int C, int G, int WS, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, int *ticket)
 {
-  static_assert((G & (G - 1)) == 0 && G >= 1 && G <= 32, "G must be a power of two <= 32");
+  static_assert(G >= 1 && G <= 32, "1..32 lanes per instance");
+  constexpr int IPW = 32 / G;   // instances per warp (lanes IPW*G..31 are spare when 32 % G != 0)
   static_assert(WS == 0 || ((G - 1) * C < WS && WS <= G * C), "band does not tile into G x C");
   constexpr int CW = (C + 3) / 4;
 
@@ -293,7 +370,8 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
-  const int gl = lane & (G - 1);
+  const int gl = lane % G;
+  const int gw = lane / G;
   const bool is_last = (gl == G - 1);
 
   const int B = F->B, W = WS ? WS : F->W;
@@ -306,8 +384,8 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   // balanced partition of the family's instances over its CTAs (n_ctas <= n_ext)
   const int first = (int) ((long long) cta_in_fam * n_ext / n_ctas);
   const int next = (int) ((long long) (cta_in_fam + 1) * n_ext / n_ctas);
-  const int grp = (int) threadIdx.x / G;
-  const bool valid = grp < next - first;
+  const int grp = warp * IPW + gw;
+  const bool valid = (gw < IPW) && (grp < next - first);
   const int inst = valid ? first + grp : next - 1;   // padding lanes shadow the last instance
   const InstDev I = F->inst[inst];
   const uint32_t *lib2 = F->lib2, *libn = F->libn;
@@ -330,6 +408,9 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   }
 
   const int nreal = min(max(W - gl * C, 0), C);   // real (in-band) cells of this lane
+#ifndef RAMCU_EMUL
+  const long long t_begin = F->dbg_wait ? clock64() : 0;
+#endif
   int high = 0, pos = 0, thigh = 0, tpos = 0;   // ram_extend.c:900-914
   int max_row = -1, max_ext = 0, stop_row = -1;
   int r = 0;
@@ -450,12 +531,8 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       }
       // row best over the instance's G lanes
 #pragma unroll
-      for (int d = G >> 1; d >= 1; d >>= 1)
-      {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          best[a] = imax(best[a], __shfl_xor_sync(kFull, best[a], d));
-      }
+      for (int a = 0; a < 4; ++a)
+        best[a] = group_max<G>(best[a], gl, lane);
     }
 
     // ---- column sums over the family (ram_extend.c:1042-1062) -------------------------------
@@ -472,20 +549,25 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       if (lane == 0)
         s_part[par][warp] = make_int4(c[0], c[1], c[2], c[3]);
       __syncthreads();
-      sums[0] = sums[1] = sums[2] = sums[3] = 0;
-      for (int w = 0; w < nwarps; ++w)
       {
-        const int4 p = s_part[par][w];
-        sums[0] += (unsigned) p.x;
-        sums[1] += (unsigned) p.y;
-        sums[2] += (unsigned) p.z;
-        sums[3] += (unsigned) p.w;
+        const int4 p = (lane < nwarps) ? s_part[par][lane] : make_int4(0, 0, 0, 0);
+        sums[0] = (unsigned) __reduce_add_sync(kFull, p.x);
+        sums[1] = (unsigned) __reduce_add_sync(kFull, p.y);
+        sums[2] = (unsigned) __reduce_add_sync(kFull, p.z);
+        sums[3] = (unsigned) __reduce_add_sync(kFull, p.w);
       }
       if (n_ctas > 1)
       {
         if (warp == 0)
         {
-          grid_exchange(F->slots + (size_t) r * 4, n_ctas, sums, lane);
+#ifndef RAMCU_EMUL
+          const long long t_ex0 = F->dbg_wait ? clock64() : 0;
+#endif
+          grid_exchange(F->slots, n_ctas, cta_in_fam, par, (unsigned) (r + 1), sums, lane);
+#ifndef RAMCU_EMUL
+          if (F->dbg_wait && lane == 0)
+            F->dbg_wait[2 * cta_in_fam] += clock64() - t_ex0;
+#endif
           if (lane == 0)
             s_bcast[par] = make_int4((int) sums[0], (int) sums[1], (int) sums[2], (int) sums[3]);
         }
@@ -545,9 +627,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
                                                   cg, gout1, nob, bestb, idx, gl, W, B, r, tmin,
                                                   tmax);
       int kidx = (idx < kBig) ? gl * C + idx : kBig;
-#pragma unroll
-      for (int d = G >> 1; d >= 1; d >>= 1)
-        kidx = min(kidx, __shfl_xor_sync(kFull, kidx, d));
+      kidx = group_min<G>(kidx, gl, lane);
       if (bestb > high)   // record setter, ram_extend.c:1140-1150
       {
         high = bestb;
@@ -601,6 +681,10 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     }
   }
 
+#ifndef RAMCU_EMUL
+  if (F->dbg_wait && threadIdx.x == 0)
+    F->dbg_wait[2 * cta_in_fam + 1] = clock64() - t_begin;
+#endif
   // ---- write back (ram_extend.c:1234-1257) ---------------------------------------------------
   if (valid && gl == 0)
   {
@@ -614,88 +698,6 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     F->result[2] = stop_row;
     F->result[3] = max_ext;
   }
-}
-
-// Library packing: 1 byte/base (0..3 = ACGT, anything else = N) -> 2 bits/base + N bitmask.
-// Each thread converts 32 bases: two 128-bit loads, one 64-bit + one 32-bit store.
-__global__ void __launch_bounds__(256)
-pack_library_kernel(const uint8_t *__restrict__ bytes, const unsigned long long len,
-                    uint32_t *__restrict__ lib2, uint32_t *__restrict__ libn,
-                    const unsigned long long n_chunks)
-{
-  const bool aligned = ((reinterpret_cast<uintptr_t>(bytes) & 15) == 0);
-  for (unsigned long long ch = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
-       ch < n_chunks; ch += (unsigned long long) gridDim.x * blockDim.x)
-  {
-    const unsigned long long base = ch * 32;
-    uint32_t raw[8];
-    if (aligned && base + 32 <= len)
-    {
-      const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(bytes + base));
-      const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(bytes + base + 16));
-      raw[0] = v0.x; raw[1] = v0.y; raw[2] = v0.z; raw[3] = v0.w;
-      raw[4] = v1.x; raw[5] = v1.y; raw[6] = v1.z; raw[7] = v1.w;
-    }
-    else
-    {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-      {
-        uint32_t w = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-        {
-          const unsigned long long p = base + i * 4 + j;
-          const uint32_t b = (p < len) ? bytes[p] : 99u;
-          w |= b << (8 * j);
-        }
-        raw[i] = w;
-      }
-    }
-    uint32_t two[2] = {0, 0};
-    uint32_t nm = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-    {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-      {
-        const uint32_t b = (raw[i] >> (8 * j)) & 0xffu;
-        const int q = i * 4 + j;
-        const uint32_t isn = (b > 3u) ? 1u : 0u;
-        nm |= isn << q;
-        two[q >> 4] |= (b & 3u) << (2 * (q & 15));
-      }
-    }
-    *reinterpret_cast<uint2 *>(lib2 + ch * 2) = make_uint2(two[0], two[1]);
-    libn[ch] = nm;
-  }
-}
-
-
-// INT32 ALU roofline denominator: kChains independent max-plus chains per thread, one fused
-// add+max (VIADDMNMX) per chain per step, on every SM. Counted as ONE op per instruction-lane.
-constexpr int kPeakChains = 16;
-__global__ void __launch_bounds__(256)
-int32_peak_kernel(int *__restrict__ out, const int iters, const int seed)
-{
-  int x[kPeakChains];
-#pragma unroll
-  for (int k = 0; k < kPeakChains; ++k)
-    x[k] = seed + k * 7 + (int) threadIdx.x;
-  const int inc = seed | 1, floor_ = -seed;
-  for (int i = 0; i < iters; ++i)
-  {
-#pragma unroll
-    for (int k = 0; k < kPeakChains; ++k)
-      x[k] = max(x[k] + inc, floor_ + k);
-  }
-  int acc = 0;
-#pragma unroll
-  for (int k = 0; k < kPeakChains; ++k)
-    acc ^= x[k];
-  if (acc == 0x7fffffff)
-    out[0] = acc;
 }
 
 }  // namespace ramcu

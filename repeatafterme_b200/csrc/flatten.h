@@ -59,6 +59,16 @@ static inline void flatten_cores(int direction, int n_cores, const ramcu_core_t 
                    [](const InstDev &a, const InstDev &b) { return a.tmax > b.tmax; });
 }
 
+// grid layout helpers shared by the host code and the CPU emulation driver
+static inline int inst_per_warp(int G) { return 32 / G; }
+// CTA size when n_ext instances are split evenly over n_ctas CTAs (whole warps of 32/G instances)
+static inline int cta_threads(int n_ext, int n_ctas, int G)
+{
+  const int per_cta = (n_ext + n_ctas - 1) / n_ctas;
+  const int ipw = inst_per_warp(G);
+  return 32 * ((per_cta + ipw - 1) / ipw);
+}
+
 static inline void fill_family(FamDev &f, const ramcu_scoring_t *sc, const ramcu_params_t *pr,
                                int n_ext, int n_ctas)
 {

@@ -16,7 +16,9 @@
 
 #include "../../include/ramcu.h"
 #include "extend_kernel.cuh"
+#include "aux_kernels.cuh"
 #include "flatten.h"
+#include "kernels.h"
 
 using namespace ramcu;
 
@@ -46,17 +48,7 @@ static int fail(int code, const char *fmt, ...)
 // ------------------------------------------------------------------------------------------
 // kernel registry: band tilings
 // ------------------------------------------------------------------------------------------
-typedef void (*extend_fn)(const FamDev *, const int *, int *);
-
-struct KernelCfg
-{
-  int B;    // bandwidth this instantiation is specialised for (-1 = any, runtime W)
-  int C;    // cells per lane
-  int G;    // lanes per instance
-  int maxt; // largest CTA size (threads) supported
-  extend_fn fn;
-  int regs; // filled at init
-};
+static const int kBatchThreads = 128;   // CTA size used when many families share a launch
 
 // how a family is laid out on the grid
 struct Plan
@@ -65,30 +57,16 @@ struct Plan
   int threads;  // CTA size for a launch of this family alone
 };
 
-static const int kBatchThreads = 128;   // CTA size used when many families share a launch
-
-// MAXT = largest CTA the instantiation supports; it caps registers per thread at 65536 / MAXT
-constexpr int maxt_for(int C)
+static std::vector<KernelCfg *> g_cfgs;
+static void collect_cfgs()
 {
-  return C <= 8 ? 768 : C <= 13 ? 640 : C <= 16 ? 512 : C <= 21 ? 384 : C <= 32 ? 320 : 256;
+  if (!g_cfgs.empty())
+    return;
+  const CfgList lists[] = {cfgs_b14(), cfgs_b20(), cfgs_b40(), cfgs_b60(), cfgs_b80(), cfgs_b100(), cfgs_generic()};
+  for (const CfgList &l : lists)
+    for (int i = 0; i < l.n; ++i)
+      g_cfgs.push_back(&l.cfgs[i]);
 }
-#define RAMCU_CFG(B_, C_, G_) {B_, C_, G_, maxt_for(C_), extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_)>, 0}
-#define RAMCU_GEN(C_, G_) {-1, C_, G_, maxt_for(C_), extend_kernel<C_, G_, 0, maxt_for(C_)>, 0}
-
-static KernelCfg g_cfgs[] = {
-  // RAMExtend default (ram_extend.c:247)
-  RAMCU_CFG(14, 29, 1), RAMCU_CFG(14, 15, 2), RAMCU_CFG(14, 8, 4), RAMCU_CFG(14, 4, 8),
-  RAMCU_CFG(20, 41, 1), RAMCU_CFG(20, 21, 2), RAMCU_CFG(20, 11, 4),
-  // util/extend-stk.pl:365
-  RAMCU_CFG(40, 81, 1), RAMCU_CFG(40, 41, 2), RAMCU_CFG(40, 21, 4), RAMCU_CFG(40, 11, 8),
-  RAMCU_CFG(60, 31, 4), RAMCU_CFG(60, 16, 8), RAMCU_CFG(60, 8, 16),
-  RAMCU_CFG(80, 41, 4), RAMCU_CFG(80, 21, 8),
-  RAMCU_CFG(100, 51, 4), RAMCU_CFG(100, 26, 8), RAMCU_CFG(100, 13, 16),
-  // any other bandwidth: runtime band width, fully predicated cells
-  RAMCU_GEN(4, 4), RAMCU_GEN(8, 4), RAMCU_GEN(16, 4), RAMCU_GEN(32, 4),
-  RAMCU_GEN(16, 16), RAMCU_GEN(32, 16), RAMCU_GEN(16, 32), RAMCU_GEN(32, 32),
-};
-static const int g_ncfg = (int) (sizeof(g_cfgs) / sizeof(g_cfgs[0]));
 
 // ------------------------------------------------------------------------------------------
 // objects
@@ -131,6 +109,7 @@ struct ramcu_job
   int *d_cta_fam;     // zeros, n_ctas
   unsigned char *d_forced;
   int *d_dbg_rows, *d_dbg_best, *d_dbg_sums;
+  long long *d_dbg_wait;   // RAMCU_STATS=1 diagnostics
   bool ran, timed;
 };
 
@@ -164,10 +143,11 @@ extern "C" int ramcu_init(int device, ramcu_ctx **out)
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
   CK(cudaMalloc(&c->d_ticket, sizeof(int)));
-  for (int i = 0; i < g_ncfg; ++i)
+  collect_cfgs();
+  for (KernelCfg *k : g_cfgs)
   {
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, (const void *) g_cfgs[i].fn);
+    e = cudaFuncGetAttributes(&fa, (const void *) k->fn);
     if (e != cudaSuccess)
     {
       delete c;
@@ -175,7 +155,7 @@ extern "C" int ramcu_init(int device, ramcu_ctx **out)
                   "ramcu_init: kernel image not loadable on this device (built for sm_100a): %s",
                   cudaGetErrorString(e));
     }
-    g_cfgs[i].regs = fa.numRegs;
+    k->regs = fa.numRegs;
   }
   *out = c;
   return RAMCU_OK;
@@ -351,15 +331,6 @@ extern "C" int ramcu_library_free(ramcu_ctx *c, ramcu_library *lib)
 // ------------------------------------------------------------------------------------------
 // jobs
 // ------------------------------------------------------------------------------------------
-static int round32(long long x) { return (int) (((x + 31) / 32) * 32); }
-
-// CTA size needed when n_ext instances are split evenly over n_ctas CTAs
-static int threads_for(int n_ext, int n_ctas, int G)
-{
-  const int mx = (n_ext + n_ctas - 1) / n_ctas;
-  return round32((long long) mx * G);
-}
-
 static int ctas_per_sm(const KernelCfg *k, int threads)
 {
   int nb = 0;
@@ -369,22 +340,23 @@ static int ctas_per_sm(const KernelCfg *k, int threads)
 }
 
 // Layout of one family launched on its own: a single CTA when it fits (no grid exchange at all),
-// else ~128-thread CTAs on distinct SMs, else the same number of equally loaded CTAs on every SM
-// (the column time is set by the most loaded SM, and every CTA waits for it).
+// else 4-warp CTAs on distinct SMs, else the same number of equally loaded CTAs on every SM (the
+// column time is set by the most loaded scheduler, and every CTA of the family waits for it).
 static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int n_ext, Plan *p)
 {
-  const long long lanes = (long long) n_ext * k->G;
+  const int ipw = inst_per_warp(k->G);
+  const long long warps = ((long long) n_ext + ipw - 1) / ipw;
   const int sm = c->sm_count;
-  if (lanes <= k->maxt)
+  if (warps * 32 <= k->maxt)
   {
     p->n_ctas = 1;
-    p->threads = round32(lanes);
+    p->threads = (int) warps * 32;
     return true;
   }
-  if (lanes <= (long long) sm * 128)
+  if (warps <= (long long) sm * 4)
   {
-    p->n_ctas = (int) std::min<long long>((lanes + 127) / 128, n_ext);
-    p->threads = threads_for(n_ext, p->n_ctas, k->G);
+    p->n_ctas = (int) std::min<long long>((warps + 3) / 4, n_ext);
+    p->threads = cta_threads(n_ext, p->n_ctas, k->G);
     return p->threads <= k->maxt;
   }
   for (int per_sm = 1; per_sm <= 16; ++per_sm)
@@ -392,7 +364,7 @@ static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int n_ext, Plan *p
     const long long n = (long long) sm * per_sm;
     if (n > n_ext)
       break;
-    const int t = threads_for(n_ext, (int) n, k->G);
+    const int t = cta_threads(n_ext, (int) n, k->G);
     if (t > k->maxt)
       continue;
     if (ctas_per_sm(k, t) < per_sm)
@@ -407,12 +379,8 @@ static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int n_ext, Plan *p
 // Layout when the family shares a launch with others: fixed CTA size.
 static bool plan_batch(const ramcu_ctx *c, const KernelCfg *k, int n_ext, int *n_ctas)
 {
-  const long long lanes = (long long) n_ext * k->G;
-  long long n = std::min<long long>((lanes + kBatchThreads - 1) / kBatchThreads, n_ext);
-  while (n < n_ext && threads_for(n_ext, (int) n, k->G) > kBatchThreads)
-    ++n;
-  if (threads_for(n_ext, (int) n, k->G) > kBatchThreads)
-    return false;
+  const int per_cta = (kBatchThreads / 32) * inst_per_warp(k->G);
+  const long long n = ((long long) n_ext + per_cta - 1) / per_cta;
   if (n > (long long) ctas_per_sm(k, kBatchThreads) * c->sm_count)
     return false;   // its CTAs could not all be resident: the column exchange would deadlock
   *n_ctas = (int) n;
@@ -420,17 +388,17 @@ static bool plan_batch(const ramcu_ctx *c, const KernelCfg *k, int n_ext, int *n
 }
 
 // Rough cycles per column of a family running alone (tuned on B200): a warp
-// executes about C*35 + 200 + 25*log2(G) instructions per row; one warp alone issues one every
-// ~4.5 cycles (dependent max-plus chains), a loaded scheduler one every ~2.2 cycles.
+// executes about C*35 + 450 instructions per row; one warp alone issues one every ~4.5 cycles
+// (dependent max-plus chains), a loaded scheduler one every ~2.2 cycles; the busiest of the
+// four schedulers of the busiest SM sets the pace.
 static double solo_cost(const ramcu_ctx *c, const KernelCfg *k, int n_ext, const Plan &p)
 {
-  int lg = 0;
-  while ((1 << lg) < k->G)
-    ++lg;
-  const double instr = k->C * 35.0 + 200.0 + 25.0 * lg;
-  const double warps = (double) p.n_ctas * (p.threads / 32);
-  const double per_sched = std::max(1.0, std::ceil(warps / (c->sm_count * 4.0)));
-  const double sync = p.n_ctas > 1 ? 2500.0 : 0.0;
+  const double instr = k->C * 35.0 + 450.0;
+  const int warps_per_cta = p.threads / 32;
+  const int ctas_on_sm = (p.n_ctas + c->sm_count - 1) / c->sm_count;
+  const double per_sched = std::ceil(warps_per_cta * ctas_on_sm / 4.0);
+  const double sync = p.n_ctas > 1 ? 2000.0 : 0.0;
+  (void) n_ext;
   return std::max(instr * 4.5, per_sched * instr * 2.2) + sync;
 }
 
@@ -439,19 +407,18 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force
 {
   const int W = 2 * B + 1;
   std::vector<const KernelCfg *> cand;
-  for (int i = 0; i < g_ncfg; ++i)
-    if (g_cfgs[i].B == B)
-      cand.push_back(&g_cfgs[i]);
+  for (const KernelCfg *k : g_cfgs)
+    if (k->B == B)
+      cand.push_back(k);
   if (cand.empty())
-    for (int i = 0; i < g_ncfg; ++i)
-      if (g_cfgs[i].B < 0 && g_cfgs[i].C * g_cfgs[i].G >= W &&
-          (g_cfgs[i].G - 1) * g_cfgs[i].C < W)
-        cand.push_back(&g_cfgs[i]);
+    for (const KernelCfg *k : g_cfgs)
+      if (k->B < 0 && k->C * k->G >= W && (k->G - 1) * k->C < W)
+        cand.push_back(k);
   if (cand.empty())
-    for (int i = 0; i < g_ncfg; ++i)  // narrow bands: trailing lanes may be entirely padding
-      if (g_cfgs[i].B < 0 && g_cfgs[i].C * g_cfgs[i].G >= W)
+    for (const KernelCfg *k : g_cfgs)  // narrow bands: trailing lanes may be entirely padding
+      if (k->B < 0 && k->C * k->G >= W)
       {
-        cand.push_back(&g_cfgs[i]);
+        cand.push_back(k);
         break;
       }
   std::sort(cand.begin(), cand.end(),
@@ -482,7 +449,7 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force
   return best;
 }
 
-static size_t slots_bytes(int L) { return ((size_t) L + 1) * 4 * sizeof(unsigned long long); }
+static size_t slots_bytes(int n_ctas) { return (size_t) 2 * std::max(n_ctas, 1) * 4 * sizeof(unsigned long long); }
 
 static void free_job_device(ramcu_job *j)
 {
@@ -498,6 +465,7 @@ static void free_job_device(ramcu_job *j)
   cudaFree(j->d_dbg_rows);
   cudaFree(j->d_dbg_best);
   cudaFree(j->d_dbg_sums);
+  cudaFree(j->d_dbg_wait);
 }
 
 static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
@@ -563,7 +531,7 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     CK(cudaMalloc(&j->d_thigh, inst.size() * sizeof(int)));
     CK(cudaMalloc(&j->d_tpos, inst.size() * sizeof(int)));
     CK(cudaMalloc(&j->d_result, 8 * sizeof(int)));
-    CK(cudaMalloc(&j->d_slots, slots_bytes(pr->L)));
+    CK(cudaMalloc(&j->d_slots, slots_bytes(max_ctas)));
     CK(cudaMalloc(&j->d_fam, sizeof(FamDev)));
     CK(cudaMalloc(&j->d_cta_fam, max_ctas * sizeof(int)));
     CK(cudaMemsetAsync(j->d_cta_fam, 0, max_ctas * sizeof(int), c->stream));
@@ -579,8 +547,14 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
         CK(cudaMemcpyAsync(j->d_forced, forced, dbg_rows, cudaMemcpyHostToDevice, c->stream));
       }
     }
+    if (getenv("RAMCU_STATS"))
+    {
+      CK(cudaMalloc(&j->d_dbg_wait, (size_t) 2 * max_ctas * sizeof(long long)));
+      CK(cudaMemsetAsync(j->d_dbg_wait, 0, (size_t) 2 * max_ctas * sizeof(long long), c->stream));
+    }
     FamDev &f = j->fam;
     fill_family(f, sc, pr, j->n_ext, j->n_ctas);
+    f.dbg_wait = j->d_dbg_wait;
     f.lib2 = lib->d_lib2;
     f.libn = lib->d_libn;
     f.inst = j->d_inst;
@@ -611,7 +585,7 @@ static int launch_single(ramcu_ctx *c, ramcu_job *j)
 {
   CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(int), c->stream));
   if (j->n_ctas > 1)
-    CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->pr.L), c->stream));
+    CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->solo.n_ctas), c->stream));
   j->cfg->fn<<<j->solo.n_ctas, j->solo.threads, 0, c->stream>>>(j->d_fam, j->d_cta_fam, c->d_ticket);
   CK(cudaGetLastError());
   return RAMCU_OK;
@@ -685,6 +659,23 @@ extern "C" int ramcu_job_fetch(ramcu_ctx *c, ramcu_job *j, uint8_t *master_out, 
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
       res->kernel_ms = ms;
+  }
+  if (j->d_dbg_wait)
+  {
+    std::vector<long long> w((size_t) 2 * j->solo.n_ctas);
+    CK(cudaMemcpy(w.data(), j->d_dbg_wait, w.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(j->d_dbg_wait, 0, w.size() * sizeof(long long)));
+    long long wmin = 1LL << 62, wmax = 0, wsum = 0, tmax = 0;
+    for (int i = 0; i < j->solo.n_ctas; ++i)
+    {
+      wmin = std::min(wmin, w[2 * i]);
+      wmax = std::max(wmax, w[2 * i]);
+      wsum += w[2 * i];
+      tmax = std::max(tmax, w[2 * i + 1]);
+    }
+    fprintf(stderr, "[ramcu stats] ctas=%d rows=%d cycles/row: total %.0f, exchange wait min %.0f avg %.0f max %.0f\n",
+            j->solo.n_ctas, r4[1], (double) tmax / std::max(r4[1], 1), (double) wmin / std::max(r4[1], 1),
+            (double) wsum / j->solo.n_ctas / std::max(r4[1], 1), (double) wmax / std::max(r4[1], 1));
   }
   if (master_out && r4[1] > 0)
     CK(cudaMemcpy(master_out, j->d_master, r4[1], cudaMemcpyDeviceToHost));
@@ -779,7 +770,7 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
         cta_fam.push_back((int) fams.size());
       fams.push_back(f);
       if (j->batch_ctas > 1)
-        CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->pr.L), c->stream));
+        CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->batch_ctas), c->stream));
       ++q;
     }
     FamDev *d_fams = nullptr;

@@ -9,6 +9,7 @@
 
 #include "cuda_emul.h"
 #include "../../repeatafterme_b200/csrc/extend_kernel.cuh"
+#include "../../repeatafterme_b200/csrc/aux_kernels.cuh"
 #include "../../repeatafterme_b200/csrc/flatten.h"
 
 thread_local dim3e threadIdx, blockIdx, blockDim, gridDim;
@@ -89,10 +90,11 @@ static int launch(LaunchArgs proto, int grid, int block)
 struct Cfg { int C, G, WS; extend_fn fn; };
 #define ECFG(C_, G_, WS_) {C_, G_, WS_, extend_kernel<C_, G_, WS_, 1024>}
 static const Cfg kCfgs[] = {
-  ECFG(11, 1, 11), ECFG(6, 2, 11), ECFG(3, 4, 11),                     // B = 5, static band
+  ECFG(11, 1, 11), ECFG(6, 2, 11), ECFG(3, 4, 11), ECFG(4, 3, 11),      // B = 5, static band
   ECFG(29, 1, 29), ECFG(15, 2, 29), ECFG(8, 4, 29), ECFG(4, 8, 29),     // B = 14
-  ECFG(21, 4, 81), ECFG(11, 8, 81), ECFG(41, 2, 81),                    // B = 40
-  ECFG(4, 4, 0), ECFG(8, 4, 0), ECFG(16, 4, 0), ECFG(32, 4, 0), ECFG(16, 16, 0), ECFG(16, 32, 0),
+  ECFG(21, 4, 81), ECFG(11, 8, 81), ECFG(41, 2, 81), ECFG(27, 3, 81), ECFG(17, 5, 81),   // B = 40
+  ECFG(10, 3, 29), ECFG(5, 6, 29),
+  ECFG(4, 4, 0), ECFG(8, 4, 0), ECFG(16, 4, 0), ECFG(32, 4, 0), ECFG(16, 16, 0), ECFG(16, 32, 0), ECFG(8, 5, 0), ECFG(16, 7, 0),
 };
 
 extern "C" int emul_num_cfgs(void) { return (int) (sizeof(kCfgs) / sizeof(kCfgs[0])); }
@@ -143,18 +145,15 @@ extern "C" int emul_extend(int C, int G, int WS, int threads, const uint8_t *seq
     p2.L = dbg_nrows;
     p2.when_to_stop = 1 << 30;
   }
-  const int n_ctas = std::min(n_ext, (n_ext * G + threads - 1) / threads);
-  {
-    int mx = 0;
-    for (int i = 0; i < n_ctas; ++i)
-      mx = std::max(mx, (int) ((long long) (i + 1) * n_ext / n_ctas) - (int) ((long long) i * n_ext / n_ctas));
-    threads = ((mx * G + 31) / 32) * 32;
-  }
+  // `threads` is the largest CTA the caller wants; CTAs get equal shares of the instances
+  const int per_cta_max = std::max(1, (threads / 32) * inst_per_warp(G));
+  const int n_ctas = (n_ext + per_cta_max - 1) / per_cta_max;
+  threads = cta_threads(n_ext, n_ctas, G);
   std::vector<int> orig(n_ext), thigh(n_ext), tpos(n_ext), result(8, 0), cta_fam(n_ctas, 0);
   for (int i = 0; i < n_ext; ++i)
     orig[i] = inst[i].orig;
   std::vector<unsigned char> master(p2.L + 1);
-  std::vector<unsigned long long> slots((size_t) (p2.L + 1) * 4, 0);
+  std::vector<unsigned long long> slots((size_t) 2 * n_ctas * 4, 0);
   std::vector<int> drows, dbest, dsums;
   FamDev f;
   fill_family(f, sc, &p2, n_ext, n_ctas);

@@ -179,6 +179,7 @@ class Emulator:
     def __init__(self):
         src = [os.path.join(EMUL_DIR, "emul_driver.cpp"), os.path.join(EMUL_DIR, "cuda_emul.h"),
                os.path.join(ROOT, "repeatafterme_b200", "csrc", "extend_kernel.cuh"),
+               os.path.join(ROOT, "repeatafterme_b200", "csrc", "aux_kernels.cuh"),
                os.path.join(ROOT, "repeatafterme_b200", "csrc", "flatten.h")]
         path = os.path.join(EMUL_DIR, "libramemul.so")
         if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in src):

@@ -28,7 +28,7 @@ def test_golden_flat_cases_every_tiling(ramcu, oracle, name):
     lib = ramcu.upload_library(case["sequence"])
     ran = 0
     try:
-        for G in (0, 1, 2, 4, 8, 16, 32):
+        for G in (0, 1, 2, 3, 4, 5, 6, 7, 8, 16, 32):
             p = gio.params_for(case, lanes_per_instance=G)
             for d in (1, 0):
                 try:

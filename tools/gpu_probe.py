@@ -26,7 +26,7 @@ def main():
         osc = ora.scoring(matrix)
         sc = osc.to_product()
         lib = rc.upload_library(fam.sequence)
-        for G in (0, 1, 2, 4, 8, 16, 32):
+        for G in (0, 1, 2, 3, 4, 5, 6, 7, 8, 16, 32):
             p = make_params(bandwidth=B, minimprovement=27, L=20000, lanes_per_instance=G)
             for d in (1, 0):
                 try:
@@ -54,7 +54,7 @@ def main():
         t0 = time.time()
         lib = rc.upload_library(fam.sequence)
         print(f"upload+pack {1e3*(time.time()-t0):.1f} ms")
-        for G in (0, 1, 2, 4, 8):
+        for G in (0, 1, 2, 3, 4, 5, 6, 8):
             p = make_params(bandwidth=40, minimprovement=30, L=20000, lanes_per_instance=G)
             for rep in range(2):
                 tot_ms, cu = 0.0, 0.0
