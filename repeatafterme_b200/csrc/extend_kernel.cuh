@@ -59,7 +59,9 @@ struct FamDev
   int *thigh;             // out: trimmed_sequence_high_score      (per extendable instance)
   int *tpos;              // out: trimmed_sequence_high_score_pos
   int *result;            // out: [0] max_row [1] rows_processed [2] stop_row [3] max_ext
-  unsigned long long *slots;    // [2][n_ctas][4] (tag << 32 | sum) column exchange, zeroed
+  unsigned long long *slots;    // column exchange area, zeroed before each launch:
+                                // [2][n_ctas][4] (tag << 32 | sum) slots, or, for more than
+                                // kSlotMaxCtas CTAs, [L][4] (count << 48 | sum) accumulators
   const unsigned char *forced;  // debug: forced consensus per row (or NULL)
   int *dbg_rows;          // debug: [rows][n_ext][W][2]
   int *dbg_best;          // debug: [rows][n_ext][4]
@@ -329,6 +331,34 @@ __device__ __forceinline__ void grid_exchange(unsigned long long *slots, const i
     sums[a] = (unsigned) __reduce_add_sync(kFull, (int) acc[a]);
 }
 
+// Large families (more than kSlotMaxCtas CTAs): the all-to-all slot gather above would make every
+// CTA read every slot; instead column r owns four 64-bit accumulators (zeroed before the launch)
+// and every CTA adds (1 << 48 | partial) with one RED per candidate, so the arrival count travels
+// in the same word as the data: a reader that sees count == n_ctas has the complete sum in the
+// low 32 bits (mod 2^32, exactly the reference's int arithmetic). No fence, no reset.
+constexpr int kSlotMaxCtas = 40;
+
+__device__ __forceinline__ void grid_exchange_red(unsigned long long *acc_row, const int n_ctas,
+                                                  unsigned (&sums)[4], const int lane)
+{
+  unsigned lo = 0;
+  if (lane < 4)
+  {
+    const unsigned mine = (unsigned) sel4(lane, (int) sums[0], (int) sums[1], (int) sums[2], (int) sums[3]);
+    atomicAdd(acc_row + lane, (1ull << 48) | (unsigned long long) mine);
+    unsigned long long v;
+    do
+    {
+      v = ld_relaxed_u64(acc_row + lane);
+    } while ((int) (v >> 48) != n_ctas);
+    lo = (unsigned) v;
+  }
+  sums[0] = __shfl_sync(kFull, lo, 0);
+  sums[1] = __shfl_sync(kFull, lo, 1);
+  sums[2] = __shfl_sync(kFull, lo, 2);
+  sums[3] = __shfl_sync(kFull, lo, 3);
+}
+
 // per-CTA shared state: score LUT, per-warp partial column sums, broadcast sums, logical CTA id
 struct SharedBlk
 {
@@ -563,7 +593,10 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
 #ifndef RAMCU_EMUL
           const long long t_ex0 = F->dbg_wait ? clock64() : 0;
 #endif
-          grid_exchange(F->slots, n_ctas, cta_in_fam, par, (unsigned) (r + 1), sums, lane);
+          if (n_ctas > kSlotMaxCtas)
+            grid_exchange_red(F->slots + (size_t) r * 4, n_ctas, sums, lane);
+          else
+            grid_exchange(F->slots, n_ctas, cta_in_fam, par, (unsigned) (r + 1), sums, lane);
 #ifndef RAMCU_EMUL
           if (F->dbg_wait && lane == 0)
             F->dbg_wait[2 * cta_in_fam] += clock64() - t_ex0;

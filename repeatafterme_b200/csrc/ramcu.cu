@@ -449,7 +449,11 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force
   return best;
 }
 
-static size_t slots_bytes(int n_ctas) { return (size_t) 2 * std::max(n_ctas, 1) * 4 * sizeof(unsigned long long); }
+static size_t slots_bytes(int n_ctas, int L)
+{
+  const size_t words = n_ctas > kSlotMaxCtas ? ((size_t) L + 1) * 4 : (size_t) 2 * std::max(n_ctas, 1) * 4;
+  return words * sizeof(unsigned long long);
+}
 
 static void free_job_device(ramcu_job *j)
 {
@@ -531,7 +535,7 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     CK(cudaMalloc(&j->d_thigh, inst.size() * sizeof(int)));
     CK(cudaMalloc(&j->d_tpos, inst.size() * sizeof(int)));
     CK(cudaMalloc(&j->d_result, 8 * sizeof(int)));
-    CK(cudaMalloc(&j->d_slots, slots_bytes(max_ctas)));
+    CK(cudaMalloc(&j->d_slots, std::max(slots_bytes(j->solo.n_ctas, pr->L), slots_bytes(j->batch_ctas, pr->L))));
     CK(cudaMalloc(&j->d_fam, sizeof(FamDev)));
     CK(cudaMalloc(&j->d_cta_fam, max_ctas * sizeof(int)));
     CK(cudaMemsetAsync(j->d_cta_fam, 0, max_ctas * sizeof(int), c->stream));
@@ -585,7 +589,7 @@ static int launch_single(ramcu_ctx *c, ramcu_job *j)
 {
   CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(int), c->stream));
   if (j->n_ctas > 1)
-    CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->solo.n_ctas), c->stream));
+    CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->solo.n_ctas, j->pr.L), c->stream));
   j->cfg->fn<<<j->solo.n_ctas, j->solo.threads, 0, c->stream>>>(j->d_fam, j->d_cta_fam, c->d_ticket);
   CK(cudaGetLastError());
   return RAMCU_OK;
@@ -770,7 +774,7 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
         cta_fam.push_back((int) fams.size());
       fams.push_back(f);
       if (j->batch_ctas > 1)
-        CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->batch_ctas), c->stream));
+        CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->batch_ctas, j->pr.L), c->stream));
       ++q;
     }
     FamDev *d_fams = nullptr;
