@@ -25,6 +25,9 @@ constexpr int maxt_for(int C)
   return C <= 8 ? 768 : C <= 13 ? 512 : C <= 20 ? 384 : 256;
 }
 #define RAMCU_CFG(B_, C_, G_) {B_, C_, G_, maxt_for(C_), extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_)>, 0}
+// same tiling with an explicit (larger) CTA limit: fewer registers per thread, more resident
+// instances -- the capacity fallback for very large families with wide bands
+#define RAMCU_CFG_T(B_, C_, G_, T_) {B_, C_, G_, T_, extend_kernel<C_, G_, 2 * B_ + 1, T_>, 0}
 #define RAMCU_GEN(C_, G_) {-1, C_, G_, maxt_for(C_), extend_kernel<C_, G_, 0, maxt_for(C_)>, 0}
 
 struct CfgList

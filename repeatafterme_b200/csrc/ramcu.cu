@@ -393,7 +393,9 @@ static bool plan_batch(const ramcu_ctx *c, const KernelCfg *k, int n_ext, int *n
 // four schedulers of the busiest SM sets the pace.
 static double solo_cost(const ramcu_ctx *c, const KernelCfg *k, int n_ext, const Plan &p)
 {
-  const double instr = k->C * 35.0 + 450.0;
+  // a tiling squeezed below ~6 registers per cell keeps part of its rows in local memory
+  const double squeeze = (65536.0 / k->maxt) < 6.0 * k->C + 60.0 ? 1.5 : 1.0;
+  const double instr = (k->C * 35.0 + 450.0) * squeeze;
   const int warps_per_cta = p.threads / 32;
   const int ctas_on_sm = (p.n_ctas + c->sm_count - 1) / c->sm_count;
   const double per_sched = std::ceil(warps_per_cta * ctas_on_sm / 4.0);
@@ -437,7 +439,7 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force
     if (!plan_batch(c, k, n_ext, &nb))
       nb = 0;   // too large to share a launch: ramcu_batch_run launches it on its own
     // a crowded device is throughput bound: fewest lanes per instance = fewest instructions
-    const double cost = crowded ? (double) k->G : solo_cost(c, k, n_ext, p);
+    const double cost = crowded ? (double) k->G + (k->maxt > maxt_for(k->C) ? 0.5 : 0.0) : solo_cost(c, k, n_ext, p);
     if (!best || cost < best_cost)
     {
       best = k;
