@@ -181,6 +181,7 @@ def run_cuda(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/null")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rc = RamCu(local)
     stream = torch.cuda.Stream()          # a real (non-default) stream, shared with the C-ABI

@@ -337,6 +337,7 @@ __device__ __forceinline__ void grid_exchange(unsigned long long *slots, const i
 // in the same word as the data: a reader that sees count == n_ctas has the complete sum in the
 // low 32 bits (mod 2^32, exactly the reference's int arithmetic). No fence, no reset.
 constexpr int kSlotMaxCtas = 40;
+constexpr int kRedStride = 1;      // 64-bit words between the accumulators of one column
 
 __device__ __forceinline__ void grid_exchange_red(unsigned long long *acc_row, const int n_ctas,
                                                   unsigned (&sums)[4], const int lane)
@@ -345,11 +346,14 @@ __device__ __forceinline__ void grid_exchange_red(unsigned long long *acc_row, c
   if (lane < 4)
   {
     const unsigned mine = (unsigned) sel4(lane, (int) sums[0], (int) sums[1], (int) sums[2], (int) sums[3]);
-    atomicAdd(acc_row + lane, (1ull << 48) | (unsigned long long) mine);
+    // the four accumulators of a column sit in four different 128-byte lines (four L2 slices
+    // serve the REDs and the polls in parallel)
+    unsigned long long *word = acc_row + lane * kRedStride;
+    atomicAdd(word, (1ull << 48) | (unsigned long long) mine);
     unsigned long long v;
     do
     {
-      v = ld_relaxed_u64(acc_row + lane);
+      v = ld_relaxed_u64(word);
     } while ((int) (v >> 48) != n_ctas);
     lo = (unsigned) v;
   }
@@ -410,6 +414,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   const bool gaps_ok = (go <= 0) && (ge <= 0);
   const unsigned char *forced = F->forced;
   int *dbg_rows = F->dbg_rows;
+  const bool dbg_any = (F->dbg_rows != nullptr) || (F->dbg_best != nullptr);
 
   // balanced partition of the family's instances over its CTAs (n_ctas <= n_ext)
   const int first = (int) ((long long) cta_in_fam * n_ext / n_ctas);
@@ -594,7 +599,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
           const long long t_ex0 = F->dbg_wait ? clock64() : 0;
 #endif
           if (n_ctas > kSlotMaxCtas)
-            grid_exchange_red(F->slots + (size_t) r * 4, n_ctas, sums, lane);
+            grid_exchange_red(F->slots + (size_t) r * 4 * kRedStride, n_ctas, sums, lane);
           else
             grid_exchange(F->slots, n_ctas, cta_in_fam, par, (unsigned) (r + 1), sums, lane);
 #ifndef RAMCU_EMUL
@@ -630,7 +635,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       curr = (int) sums[besta];
     }
 
-    if (F->dbg_best != nullptr)
+    if (dbg_any && F->dbg_best != nullptr)
     {
       if (valid && gl == 0)
       {

@@ -143,6 +143,13 @@ extern "C" int ramcu_init(int device, ramcu_ctx **out)
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
   CK(cudaMalloc(&c->d_ticket, sizeof(int)));
+  {
+    // per-call buffers come from the stream-ordered pool; keep freed memory cached in the pool
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   collect_cfgs();
   for (KernelCfg *k : g_cfgs)
   {
@@ -271,8 +278,8 @@ static int library_pack(ramcu_ctx *c, const uint8_t *d_bytes, uint64_t length, r
   lib->length = length;
   const uint64_t n_chunks = (length + 31) / 32;  // 32 bases per chunk
   const size_t pad = 4;                           // words of slack on both sides
-  CK(cudaMalloc(&lib->alloc2, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t)));
-  CK(cudaMalloc(&lib->allocn, (n_chunks + 2 * pad) * sizeof(uint32_t)));
+  CK(cudaMallocAsync(&lib->alloc2, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t), c->stream));
+  CK(cudaMallocAsync(&lib->allocn, (n_chunks + 2 * pad) * sizeof(uint32_t), c->stream));
   CK(cudaMemsetAsync(lib->alloc2, 0, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t), c->stream));
   CK(cudaMemsetAsync(lib->allocn, 0xff, (n_chunks + 2 * pad) * sizeof(uint32_t), c->stream));
   lib->d_lib2 = (uint32_t *) lib->alloc2 + pad;
@@ -296,11 +303,11 @@ extern "C" int ramcu_library_upload(ramcu_ctx *c, const uint8_t *seq, uint64_t l
     return fail(RAMCU_ERR_ARG, "ramcu_library_upload: NULL argument");
   CK(cudaSetDevice(c->device));
   uint8_t *d_bytes = nullptr;
-  CK(cudaMalloc(&d_bytes, length ? length : 1));
+  CK(cudaMallocAsync(&d_bytes, length ? length : 1, c->stream));
   CK(cudaMemcpyAsync(d_bytes, seq, length, cudaMemcpyHostToDevice, c->stream));
   int rc = library_pack(c, d_bytes, length, out);
-  cudaStreamSynchronize(c->stream);
-  cudaFree(d_bytes);
+  CK(cudaFreeAsync(d_bytes, c->stream));
+  CK(cudaStreamSynchronize(c->stream));   // the caller may reuse / free its host buffer
   return rc;
 }
 
@@ -320,10 +327,14 @@ extern "C" int ramcu_library_free(ramcu_ctx *c, ramcu_library *lib)
   if (c)
   {
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    cudaFreeAsync(lib->alloc2, c->stream);
+    cudaFreeAsync(lib->allocn, c->stream);
   }
-  cudaFree(lib->alloc2);
-  cudaFree(lib->allocn);
+  else
+  {
+    cudaFree(lib->alloc2);
+    cudaFree(lib->allocn);
+  }
   delete lib;
   return RAMCU_OK;
 }
@@ -453,25 +464,22 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force
 
 static size_t slots_bytes(int n_ctas, int L)
 {
-  const size_t words = n_ctas > kSlotMaxCtas ? ((size_t) L + 1) * 4 : (size_t) 2 * std::max(n_ctas, 1) * 4;
+  const size_t words = n_ctas > kSlotMaxCtas ? ((size_t) L + 1) * 4 * kRedStride : (size_t) 2 * std::max(n_ctas, 1) * 4;
   return words * sizeof(unsigned long long);
 }
 
-static void free_job_device(ramcu_job *j)
+static void free_job_device(ramcu_ctx *c, ramcu_job *j)
 {
-  cudaFree(j->d_inst);
-  cudaFree(j->d_master);
-  cudaFree(j->d_thigh);
-  cudaFree(j->d_tpos);
-  cudaFree(j->d_result);
-  cudaFree(j->d_slots);
-  cudaFree(j->d_fam);
-  cudaFree(j->d_cta_fam);
-  cudaFree(j->d_forced);
-  cudaFree(j->d_dbg_rows);
-  cudaFree(j->d_dbg_best);
-  cudaFree(j->d_dbg_sums);
-  cudaFree(j->d_dbg_wait);
+  void *ptrs[] = {j->d_inst, j->d_master, j->d_thigh, j->d_tpos, j->d_result, j->d_slots, j->d_fam,
+                  j->d_cta_fam, j->d_forced, j->d_dbg_rows, j->d_dbg_best, j->d_dbg_sums, j->d_dbg_wait};
+  for (void *p : ptrs)
+    if (p)
+    {
+      if (c)
+        cudaFreeAsync(p, c->stream);
+      else
+        cudaFree(p);
+    }
 }
 
 static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
@@ -530,32 +538,32 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     const int max_ctas = std::max(j->solo.n_ctas, j->batch_ctas);
 
     const int W = 2 * B + 1;
-    CK(cudaMalloc(&j->d_inst, inst.size() * sizeof(InstDev)));
+    CK(cudaMallocAsync(&j->d_inst, inst.size() * sizeof(InstDev), c->stream));
     CK(cudaMemcpyAsync(j->d_inst, inst.data(), inst.size() * sizeof(InstDev),
                        cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMalloc(&j->d_master, std::max(pr->L, 1)));
-    CK(cudaMalloc(&j->d_thigh, inst.size() * sizeof(int)));
-    CK(cudaMalloc(&j->d_tpos, inst.size() * sizeof(int)));
-    CK(cudaMalloc(&j->d_result, 8 * sizeof(int)));
-    CK(cudaMalloc(&j->d_slots, std::max(slots_bytes(j->solo.n_ctas, pr->L), slots_bytes(j->batch_ctas, pr->L))));
-    CK(cudaMalloc(&j->d_fam, sizeof(FamDev)));
-    CK(cudaMalloc(&j->d_cta_fam, max_ctas * sizeof(int)));
+    CK(cudaMallocAsync(&j->d_master, std::max(pr->L, 1), c->stream));
+    CK(cudaMallocAsync(&j->d_thigh, inst.size() * sizeof(int), c->stream));
+    CK(cudaMallocAsync(&j->d_tpos, inst.size() * sizeof(int), c->stream));
+    CK(cudaMallocAsync(&j->d_result, 8 * sizeof(int), c->stream));
+    CK(cudaMallocAsync(&j->d_slots, std::max(slots_bytes(j->solo.n_ctas, pr->L), slots_bytes(j->batch_ctas, pr->L)), c->stream));
+    CK(cudaMallocAsync(&j->d_fam, sizeof(FamDev), c->stream));
+    CK(cudaMallocAsync(&j->d_cta_fam, max_ctas * sizeof(int), c->stream));
     CK(cudaMemsetAsync(j->d_cta_fam, 0, max_ctas * sizeof(int), c->stream));
     if (dbg_rows > 0)
     {
-      CK(cudaMalloc(&j->d_dbg_rows, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int)));
-      CK(cudaMalloc(&j->d_dbg_best, (size_t) dbg_rows * j->n_ext * 4 * sizeof(int)));
-      CK(cudaMalloc(&j->d_dbg_sums, (size_t) dbg_rows * 4 * sizeof(int)));
+      CK(cudaMallocAsync(&j->d_dbg_rows, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int), c->stream));
+      CK(cudaMallocAsync(&j->d_dbg_best, (size_t) dbg_rows * j->n_ext * 4 * sizeof(int), c->stream));
+      CK(cudaMallocAsync(&j->d_dbg_sums, (size_t) dbg_rows * 4 * sizeof(int), c->stream));
       CK(cudaMemsetAsync(j->d_dbg_rows, 0, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int), c->stream));
       if (forced)
       {
-        CK(cudaMalloc(&j->d_forced, dbg_rows));
+        CK(cudaMallocAsync(&j->d_forced, dbg_rows, c->stream));
         CK(cudaMemcpyAsync(j->d_forced, forced, dbg_rows, cudaMemcpyHostToDevice, c->stream));
       }
     }
     if (getenv("RAMCU_STATS"))
     {
-      CK(cudaMalloc(&j->d_dbg_wait, (size_t) 2 * max_ctas * sizeof(long long)));
+      CK(cudaMallocAsync(&j->d_dbg_wait, (size_t) 2 * max_ctas * sizeof(long long), c->stream));
       CK(cudaMemsetAsync(j->d_dbg_wait, 0, (size_t) 2 * max_ctas * sizeof(long long), c->stream));
     }
     FamDev &f = j->fam;
@@ -700,11 +708,8 @@ extern "C" int ramcu_job_free(ramcu_ctx *c, ramcu_job *j)
   if (!j)
     return RAMCU_OK;
   if (c)
-  {
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-  }
-  free_job_device(j);
+  free_job_device(c, j);
   delete j;
   return RAMCU_OK;
 }

@@ -153,7 +153,7 @@ extern "C" int emul_extend(int C, int G, int WS, int threads, const uint8_t *seq
   for (int i = 0; i < n_ext; ++i)
     orig[i] = inst[i].orig;
   std::vector<unsigned char> master(p2.L + 1);
-  std::vector<unsigned long long> slots(std::max((size_t) 2 * n_ctas * 4, (size_t) (p2.L + 1) * 4), 0);
+  std::vector<unsigned long long> slots(std::max((size_t) 2 * n_ctas * 4, (size_t) (p2.L + 1) * 4 * kRedStride), 0);
   std::vector<int> drows, dbest, dsums;
   FamDev f;
   fill_family(f, sc, &p2, n_ext, n_ctas);
