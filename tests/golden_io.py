@@ -17,7 +17,14 @@ def flat_case_names():
 
 
 def cli_case_names():
-    return sorted(os.path.basename(p)[4:] for p in glob.glob(os.path.join(GOLDEN, "cli_*")))
+    """CLI cases whose inputs are committed (the ce10 stand-in cases regenerate theirs)"""
+    return sorted(os.path.basename(p)[4:] for p in glob.glob(os.path.join(GOLDEN, "cli_*"))
+                  if os.path.exists(os.path.join(p, "input.npz")))
+
+
+def load_cli_outputs(name):
+    d = os.path.join(GOLDEN, f"cli_{name}")
+    return {f: open(os.path.join(d, f)).read() for f in ("stdout.txt", "out.tsv", "out.fa", "cons.fa")}
 
 
 def load_flat(name):

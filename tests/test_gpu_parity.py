@@ -225,3 +225,33 @@ def test_cli_outputs_byte_identical(name, tmp_path):
     for f in ("out.tsv", "out.fa", "cons.fa"):
         p = tmp_path / f
         assert (p.read_text() if p.exists() else "") == case["want"][f], f
+
+
+@pytest.fixture(scope="module")
+def ce10_standin(tmp_path_factory):
+    from tests import ce10_standin as cs
+    d = tmp_path_factory.mktemp("ce10")
+    twobit, tsvs = cs.build(str(d))
+    return str(d), twobit, tsvs
+
+
+@pytest.mark.parametrize("fam", [1, 2, 3])
+def test_ce10_families_cli_byte_identical(ce10_standin, fam):
+    """BASELINE configs 2-3: the extend-stk.pl command line (util/extend-stk.pl:365: -L 20000
+    -bandwidth 40 -matrix 14p43g -minimprovement 30 -vvv) on test/ce10-fam{1,2,3}.stk, against a
+    deterministic stand-in for the missing ce10.2bit; outputs of the reference binary are golden."""
+    exe = os.path.join(ROOT, "repeatafterme_b200", "bin", "RAMExtend")
+    if not os.path.exists(exe):
+        pytest.skip("bin/RAMExtend not built (needs the reference's host objects)")
+    from tests import ce10_standin as cs
+    from tests.cases import filter_stdout
+    d, twobit, tsvs = ce10_standin
+    want = gio.load_cli_outputs(f"ce10_fam{fam}")
+    outs = {f: os.path.join(d, f"fam{fam}_{f}") for f in ("out.tsv", "out.fa", "cons.fa")}
+    cmd = [exe, "-twobit", twobit, "-ranges", tsvs[fam], "-outtsv", outs["out.tsv"], "-outfa", outs["out.fa"],
+           "-cons", outs["cons.fa"]] + cs.STK_FLAGS
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr
+    assert filter_stdout(r.stdout, d) == want["stdout.txt"]
+    for f, p in outs.items():
+        assert (open(p).read() if os.path.exists(p) else "") == want[f], f
