@@ -311,6 +311,11 @@ def run_cuda(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_extend_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
 
     cpu = None
     if world == 1 or rank == 0:
@@ -334,7 +339,8 @@ def run_cuda(args):
                                         "on all SMs, one op per instruction-lane)",
                          "nominal_peak": round(NOMINAL_INT32_GOPS, 1),
                          "frac_of_nominal": round(per_gpu_gops / NOMINAL_INT32_GOPS, 4),
-                         "ops_per_cell_update": OPS_PER_CU, "traffic": None,
+                         "ops_per_cell_update": OPS_PER_CU, "traffic": traffic,
+                         "traffic_unit": "DRAM bytes per extend_kernel launch (ncu, config 4)",
                          "hbm": {"achieved": round(flank_bytes * args.steps / (dev_ms * 1e-3) / 1e9, 3),
                                  "peak": hbm_peak, "unit": "GB/s",
                                  "note": "algorithmic flank bytes (2 bits per base per instance-row); the path is "
