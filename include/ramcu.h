@@ -123,6 +123,27 @@ int ramcu_library_upload(ramcu_ctx *ctx, const uint8_t *seq_bytes, uint64_t leng
 /* Same, but seq_bytes is already a DEVICE pointer (no host<->device copy). */
 int ramcu_library_from_device(ramcu_ctx *ctx, const uint8_t *d_seq_bytes, uint64_t length,
                               ramcu_library **out);
+/* 2bit-native upload (the flank feed without the byte expansion of sequence.c:752-822): `blob`
+ * holds packed DNA exactly as stored in a .2bit record (kentsrc/twoBitNew.c:571-582: 4 bases per
+ * byte, first base in the top bits, T0 C1 A2 G3). Each window copies `len` bases starting at base
+ * `src_base` of the record whose packed DNA starts at byte `src_byte` of the blob to library
+ * positions [dst, dst+len); windows must tile [0, total_length) in increasing dst order (the
+ * concatenation loadSequenceSubsetMinimal builds). N ranges (the record's N-blocks clipped to the
+ * windows) are given in library coordinates. HOST pointers. */
+typedef struct
+{
+  uint64_t dst;
+  uint64_t len;
+  uint64_t src_byte;
+  uint64_t src_base;
+} ramcu_window_t;
+int ramcu_library_from_twobit(ramcu_ctx *ctx, const uint8_t *blob, uint64_t blob_bytes,
+                              int n_windows, const ramcu_window_t *windows, int n_nranges,
+                              const uint64_t *n_start, const uint64_t *n_len,
+                              uint64_t total_length, ramcu_library **out);
+/* Test aid: copy the packed device library back (lib2: 2 bits/base, 16 bases per word,
+ * A0 C1 G2 T3; libn: N bitmask, 32 bases per word). Sizes: ceil(len/32)*2 and ceil(len/32) words. */
+int ramcu_library_download(ramcu_ctx *ctx, ramcu_library *lib, uint32_t *lib2_out, uint32_t *libn_out);
 int ramcu_library_free(ramcu_ctx *ctx, ramcu_library *lib);
 
 /* One call == one call of the reference's extend_alignment() for `direction` (1 = right,

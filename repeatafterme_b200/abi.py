@@ -34,7 +34,7 @@ NCODES = 5  # A,C,G,T,N
 ABI_SYMBOLS = (
     "ramcu_last_error", "ramcu_abi_version", "ramcu_init", "ramcu_destroy", "ramcu_set_stream",
     "ramcu_device_info", "ramcu_int32_peak", "ramcu_scoring_by_name", "ramcu_library_upload",
-    "ramcu_library_from_device", "ramcu_library_free", "ramcu_extend", "ramcu_job_create",
+    "ramcu_library_from_device", "ramcu_library_from_twobit", "ramcu_library_download", "ramcu_library_free", "ramcu_extend", "ramcu_job_create",
     "ramcu_job_run", "ramcu_job_fetch", "ramcu_job_free", "ramcu_batch_run", "ramcu_debug_rows",
 )
 
@@ -126,6 +126,8 @@ def load_ramcu(path: str = LIB_PATH) -> C.CDLL:
     lib.ramcu_int32_peak.argtypes = [vp, P(C.c_double), P(C.c_double)]
     lib.ramcu_library_upload.argtypes = [vp, vp, u64, P(vp)]
     lib.ramcu_library_from_device.argtypes = [vp, vp, u64, P(vp)]
+    lib.ramcu_library_from_twobit.argtypes = [vp, vp, u64, i32, vp, i32, vp, vp, u64, P(vp)]
+    lib.ramcu_library_download.argtypes = [vp, vp, vp, vp]
     lib.ramcu_library_free.argtypes = [vp, vp]
     lib.ramcu_extend.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult)]
     lib.ramcu_job_create.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), P(vp)]
@@ -203,6 +205,25 @@ class RamCu:
         h = C.c_void_p()
         self._check(self.lib.ramcu_library_from_device(self.ctx, C.c_void_p(dev_ptr), length, C.byref(h)))
         return h
+
+    def library_from_twobit(self, blob: np.ndarray, windows: np.ndarray, n_start, n_len, total: int) -> C.c_void_p:
+        """windows: uint64 array [n][4] = (dst, len, src_byte, src_base); see ramcu_library_from_twobit"""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        windows = np.ascontiguousarray(windows, dtype=np.uint64).reshape(-1, 4)
+        n_start = np.ascontiguousarray(n_start, dtype=np.uint64)
+        n_len = np.ascontiguousarray(n_len, dtype=np.uint64)
+        h = C.c_void_p()
+        self._check(self.lib.ramcu_library_from_twobit(self.ctx, blob.ctypes.data, blob.size, windows.shape[0],
+                                                       windows.ctypes.data, n_start.size, n_start.ctypes.data,
+                                                       n_len.ctypes.data, total, C.byref(h)))
+        return h
+
+    def download_library(self, h, length: int):
+        n = (length + 31) // 32
+        lib2 = np.zeros(2 * n, dtype=np.uint32)
+        libn = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.ramcu_library_download(self.ctx, h, lib2.ctypes.data, libn.ctypes.data))
+        return lib2, libn
 
     def free_library(self, h):
         self._check(self.lib.ramcu_library_free(self.ctx, h))

@@ -62,6 +62,115 @@ pack_library_kernel(const uint8_t *__restrict__ bytes, const unsigned long long 
 }
 
 
+// 2bit-native flank feed: build the packed library straight from the .2bit file's own packed DNA
+// (kentsrc/twoBitNew.c:571-582: 4 bases per byte, first base in the top two bits, T0 C1 A2 G3),
+// without the 1-byte-per-base expansion of loadSequenceSubsetMinimal (sequence.c:752-822).
+// One thread produces 32 library bases: it finds its window (binary search over dst offsets), reads
+// the <= 12 source bytes that cover them as three 32-bit words, re-orders the bases to the little
+// endian A0 C1 G2 T3 code of lib2 and stores one 64-bit word. N-blocks are applied by
+// nmask_ranges_kernel afterwards.
+struct WindowDev
+{
+  unsigned long long dst;      // first library position of the window
+  unsigned long long len;      // bases
+  unsigned long long src_byte; // byte offset of the record's packed DNA inside the blob
+  unsigned long long src_base; // index of the window's first base inside the record
+};
+
+__global__ void __launch_bounds__(256)
+twobit_windows_kernel(const uint8_t *__restrict__ blob, const unsigned long long blob_bytes,
+                      const WindowDev *__restrict__ win, const int n_win,
+                      const unsigned long long total, uint32_t *__restrict__ lib2,
+                      const unsigned long long n_chunks)
+{
+  for (unsigned long long ch = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+       ch < n_chunks; ch += (unsigned long long) gridDim.x * blockDim.x)
+  {
+    const unsigned long long base = ch * 32;
+    uint32_t two[2] = {0, 0};
+    // window containing `base` (windows tile [0,total) in dst order)
+    int lo = 0, hi = n_win - 1;
+    while (lo < hi)
+    {
+      const int mid = (lo + hi + 1) >> 1;
+      if (win[mid].dst <= base)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+    int w = lo;
+    unsigned long long p = base;
+    const unsigned long long end = min(base + 32, total);
+    while (p < end)
+    {
+      while (w + 1 < n_win && win[w + 1].dst <= p)
+        ++w;
+      const WindowDev W = win[w];
+      const unsigned long long wend = min(end, W.dst + W.len);
+      if (wend <= p)
+      {
+        ++p;     // hole between windows (not produced by the loader): leave code 0
+        continue;
+      }
+      // source bases [sb, sb + n) of the record
+      const unsigned long long sb = W.src_base + (p - W.dst);
+      const int n = (int) (wend - p);
+      const unsigned long long b0 = W.src_byte + (sb >> 2);          // first source byte
+      const unsigned long long a0 = b0 & ~3ull;                      // aligned down to 4 bytes
+      uint32_t raw[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        const unsigned long long a = a0 + 4ull * i;
+        raw[i] = (a + 4 <= blob_bytes) ? __ldg(reinterpret_cast<const uint32_t *>(blob + a)) : 0u;
+        if (a + 4 > blob_bytes && a < blob_bytes)
+        {
+          uint32_t v = 0;
+          for (unsigned long long q = a; q < blob_bytes; ++q)
+            v |= (uint32_t) blob[q] << (8 * (q - a));
+          raw[i] = v;
+        }
+      }
+      const int first = (int) ((b0 - a0) * 4 + (sb & 3));            // base index inside raw[]
+      for (int i = 0; i < n; ++i)
+      {
+        const int bi = first + i;
+        const uint32_t byte = (raw[bi >> 4] >> (8 * ((bi >> 2) & 3))) & 0xffu;
+        const uint32_t t = (byte >> (6 - 2 * (bi & 3))) & 3u;         // T0 C1 A2 G3
+        const uint32_t code = (0x87u >> (2 * t)) & 3u;                // -> A0 C1 G2 T3 (3,1,0,2)
+        const int q = (int) (p - base) + i;
+        two[q >> 4] |= code << (2 * (q & 15));
+      }
+      p = wend;
+    }
+    *reinterpret_cast<uint2 *>(lib2 + ch * 2) = make_uint2(two[0], two[1]);
+  }
+}
+
+// set the N bit of every base in [start, start+len) for a list of ranges (library coordinates)
+__global__ void __launch_bounds__(128)
+nmask_ranges_kernel(const unsigned long long *__restrict__ start,
+                    const unsigned long long *__restrict__ len, const int n_ranges,
+                    uint32_t *__restrict__ libn)
+{
+  const int r = blockIdx.x;
+  if (r >= n_ranges)
+    return;
+  const unsigned long long s = start[r], e = s + len[r];
+  if (e <= s)
+    return;
+  const unsigned long long w0 = s >> 5, w1 = (e - 1) >> 5;
+  for (unsigned long long w = w0 + threadIdx.x; w <= w1; w += blockDim.x)
+  {
+    uint32_t m = 0xffffffffu;
+    if (w == w0)
+      m &= 0xffffffffu << (s & 31);
+    if (w == w1)
+      m &= 0xffffffffu >> (31 - ((e - 1) & 31));
+    atomicOr(libn + w, m);
+  }
+}
+
 // INT32 ALU roofline denominator: kChains independent max-plus chains per thread, one fused
 // add+max (VIADDMNMX) per chain per step, on every SM. Counted as ONE op per instruction-lane.
 constexpr int kPeakChains = 16;

@@ -320,6 +320,106 @@ extern "C" int ramcu_library_from_device(ramcu_ctx *c, const uint8_t *d_seq, uin
   return library_pack(c, d_seq, length, out);
 }
 
+static_assert(sizeof(ramcu_window_t) == sizeof(WindowDev), "window layout");
+
+extern "C" int ramcu_library_from_twobit(ramcu_ctx *c, const uint8_t *blob, uint64_t blob_bytes,
+                                         int n_windows, const ramcu_window_t *windows,
+                                         int n_nranges, const uint64_t *n_start,
+                                         const uint64_t *n_len, uint64_t total, ramcu_library **out)
+{
+  if (!c || !out || (!blob && blob_bytes) || (n_windows > 0 && !windows) || n_windows < 0 ||
+      n_nranges < 0 || (n_nranges > 0 && (!n_start || !n_len)))
+    return fail(RAMCU_ERR_ARG, "ramcu_library_from_twobit: invalid argument");
+  uint64_t expect = 0;
+  for (int i = 0; i < n_windows; ++i)
+  {
+    if (windows[i].dst != expect)
+      return fail(RAMCU_ERR_ARG, "ramcu_library_from_twobit: windows must tile the library in order "
+                  "(window %d starts at %llu, expected %llu)", i, (unsigned long long) windows[i].dst,
+                  (unsigned long long) expect);
+    if (windows[i].src_byte + (windows[i].src_base + windows[i].len + 3) / 4 > blob_bytes)
+      return fail(RAMCU_ERR_ARG, "ramcu_library_from_twobit: window %d reads past the blob", i);
+    expect += windows[i].len;
+  }
+  if (expect != total)
+    return fail(RAMCU_ERR_ARG, "ramcu_library_from_twobit: windows cover %llu of %llu bases",
+                (unsigned long long) expect, (unsigned long long) total);
+  for (int i = 0; i < n_nranges; ++i)
+    if (n_start[i] + n_len[i] > total)
+      return fail(RAMCU_ERR_ARG, "ramcu_library_from_twobit: N range %d outside the library", i);
+  CK(cudaSetDevice(c->device));
+  ramcu_library *lib = new ramcu_library();
+  lib->length = total;
+  const uint64_t n_chunks = (total + 31) / 32;
+  const size_t pad = 4;
+  uint8_t *d_blob = nullptr;
+  WindowDev *d_win = nullptr;
+  unsigned long long *d_ns = nullptr, *d_nl = nullptr;
+  CK(cudaMallocAsync(&lib->alloc2, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t), c->stream));
+  CK(cudaMallocAsync(&lib->allocn, (n_chunks + 2 * pad) * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(lib->alloc2, 0, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(lib->allocn, 0xff, (n_chunks + 2 * pad) * sizeof(uint32_t), c->stream));
+  lib->d_lib2 = (uint32_t *) lib->alloc2 + pad;
+  lib->d_libn = (uint32_t *) lib->allocn + pad;
+  if (n_chunks > 0)
+  {
+    // the tail bits of the last mask word stay set (positions past the library read as N)
+    CK(cudaMemsetAsync(lib->d_libn, 0, n_chunks * sizeof(uint32_t), c->stream));
+    CK(cudaMallocAsync(&d_blob, blob_bytes ? blob_bytes : 1, c->stream));
+    CK(cudaMemcpyAsync(d_blob, blob, blob_bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMallocAsync(&d_win, (size_t) std::max(n_windows, 1) * sizeof(WindowDev), c->stream));
+    CK(cudaMemcpyAsync(d_win, windows, (size_t) n_windows * sizeof(WindowDev), cudaMemcpyHostToDevice, c->stream));
+    const unsigned long long want = (n_chunks + 255) / 256;
+    const int grid = (int) std::min<unsigned long long>(want, (unsigned long long) c->sm_count * 16);
+    twobit_windows_kernel<<<grid, 256, 0, c->stream>>>(d_blob, blob_bytes, d_win, n_windows, total,
+                                                       lib->d_lib2, n_chunks);
+    CK(cudaGetLastError());
+    // positions past `total` inside the last chunk are N
+    if (total & 31)
+    {
+      const unsigned long long s0 = total, l0 = 32 - (total & 31);
+      CK(cudaMallocAsync(&d_ns, 2 * sizeof(unsigned long long), c->stream));
+      const unsigned long long tail[2] = {s0, l0};
+      CK(cudaMemcpyAsync(d_ns, tail, sizeof(tail), cudaMemcpyHostToDevice, c->stream));
+      nmask_ranges_kernel<<<1, 128, 0, c->stream>>>(d_ns, d_ns + 1, 1, lib->d_libn);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(c->stream));   // `tail` is on the stack
+      CK(cudaFreeAsync(d_ns, c->stream));
+      d_ns = nullptr;
+    }
+    if (n_nranges > 0)
+    {
+      CK(cudaMallocAsync(&d_ns, (size_t) n_nranges * sizeof(unsigned long long), c->stream));
+      CK(cudaMallocAsync(&d_nl, (size_t) n_nranges * sizeof(unsigned long long), c->stream));
+      CK(cudaMemcpyAsync(d_ns, n_start, (size_t) n_nranges * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(d_nl, n_len, (size_t) n_nranges * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+      nmask_ranges_kernel<<<n_nranges, 128, 0, c->stream>>>(d_ns, d_nl, n_nranges, lib->d_libn);
+      CK(cudaGetLastError());
+      CK(cudaFreeAsync(d_ns, c->stream));
+      CK(cudaFreeAsync(d_nl, c->stream));
+    }
+    CK(cudaFreeAsync(d_blob, c->stream));
+    CK(cudaFreeAsync(d_win, c->stream));
+    CK(cudaStreamSynchronize(c->stream));   // the caller may reuse its host buffers
+  }
+  *out = lib;
+  return RAMCU_OK;
+}
+
+extern "C" int ramcu_library_download(ramcu_ctx *c, ramcu_library *lib, uint32_t *lib2_out, uint32_t *libn_out)
+{
+  if (!c || !lib)
+    return fail(RAMCU_ERR_ARG, "ramcu_library_download: NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  const uint64_t n_chunks = (lib->length + 31) / 32;
+  if (lib2_out)
+    CK(cudaMemcpy(lib2_out, lib->d_lib2, n_chunks * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (libn_out)
+    CK(cudaMemcpy(libn_out, lib->d_libn, n_chunks * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return RAMCU_OK;
+}
+
 extern "C" int ramcu_library_free(ramcu_ctx *c, ramcu_library *lib)
 {
   if (!lib)

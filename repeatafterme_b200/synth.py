@@ -28,6 +28,7 @@ class Family:
     seqs: list = field(default_factory=list)        # full 2bit sequence (uint8 codes) per core
     bed: list = field(default_factory=list)         # (name, start, end, left_flag, right_flag, strand)
     params: dict = field(default_factory=dict)      # bandwidth / matrix / minimprovement / L ...
+    spans: list = field(default_factory=list)       # (window start, window end) of every core inside its 2bit sequence
 
     @property
     def n(self) -> int:
@@ -77,7 +78,7 @@ def make_family(seed: int, n: int, flank: int, divergence: float = 0.15, core_le
     anc = rng.integers(0, 4, size=2 * flank + core_len, dtype=np.uint8)
     left_anc, core, right_anc = anc[:flank], anc[flank:flank + core_len], anc[flank + core_len:]
     cores = np.zeros(n, dtype=CORE_DTYPE)
-    windows, names, seqs, bed = [], [], [], []
+    windows, names, seqs, bed, spans = [], [], [], [], []
     off = 0
     for i in range(n):
         lf = mutate(rng, left_anc, divergence)
@@ -124,12 +125,13 @@ def make_family(seed: int, n: int, flank: int, divergence: float = 0.15, core_le
             c["right_seq_pos"] = off + lower_flank + core_len - 1
         off += win.size
         windows.append(win)
+        spans.append((int(w_lo), int(w_hi)))
         name = "s%07d" % i
         names.append(name)
         seqs.append(full)
         bed.append((name, start, end, lflag, rflag, "-" if rev else "+"))
     return Family(sequence=np.concatenate(windows), cores=cores, names=names, seqs=seqs, bed=bed,
-                  params=dict(params or {}))
+                  params=dict(params or {}), spans=spans)
 
 
 def config4(seed: int = 4, n: int = 10000, flank: int = 5000) -> Family:
@@ -248,3 +250,33 @@ def read_twobit(path: str):
             s[a:a + b] = 99
         seqs.append(s)
     return names, seqs
+
+
+def pack_twobit_record(seq: np.ndarray) -> np.ndarray:
+    """packed DNA of one .2bit record: 4 bases per byte, first base in the top two bits, T0 C1 A2 G3
+    (N positions are stored as T, as UCSC's faToTwoBit does)"""
+    seq = np.asarray(seq, dtype=np.uint8)
+    codes = np.where(seq > 3, 0, _RAM_TO_2BIT[np.minimum(seq, 3)]).astype(np.uint8)
+    codes = np.concatenate([codes, np.zeros((-codes.size) % 4, dtype=np.uint8)]).reshape(-1, 4)
+    return ((codes[:, 0] << 6) | (codes[:, 1] << 4) | (codes[:, 2] << 2) | codes[:, 3]).astype(np.uint8)
+
+
+def family_twobit_windows(fam: Family):
+    """What a 2bit-native loader hands to ramcu_library_from_twobit for this family: the packed DNA
+    of every record, one window per core (the span loadSequenceSubsetMinimal would extract) and the
+    N-blocks clipped to the windows, in library coordinates."""
+    blobs, wins, n_start, n_len = [], [], [], []
+    off_bytes, dst = 0, 0
+    for full, (lo, hi) in zip(fam.seqs, fam.spans):
+        rec = pack_twobit_record(full)
+        wins.append((dst, hi - lo, off_bytes, lo))
+        isn = np.asarray(full[lo:hi]) > 3
+        d = np.diff(np.concatenate([[0], isn.astype(np.int8), [0]]))
+        for a, b in zip(np.flatnonzero(d == 1), np.flatnonzero(d == -1)):
+            n_start.append(dst + int(a))
+            n_len.append(int(b - a))
+        blobs.append(rec)
+        off_bytes += rec.size
+        dst += hi - lo
+    return (np.concatenate(blobs), np.array(wins, dtype=np.uint64), np.array(n_start, dtype=np.uint64),
+            np.array(n_len, dtype=np.uint64), dst)

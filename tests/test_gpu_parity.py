@@ -255,3 +255,38 @@ def test_ce10_families_cli_byte_identical(ce10_standin, fam):
     assert filter_stdout(r.stdout, d) == want["stdout.txt"]
     for f, p in outs.items():
         assert (open(p).read() if os.path.exists(p) else "") == want[f], f
+
+
+def _decode_packed(lib2, libn, n):
+    i = np.arange(n)
+    c = (lib2[i >> 4] >> (2 * (i & 15)).astype(np.uint32)) & 3
+    isn = (libn[i >> 5] >> (i & 31).astype(np.uint32)) & 1
+    return np.where(isn == 1, 99, c).astype(np.uint8)
+
+
+@pytest.mark.parametrize("seed,kw", [(201, dict(n_frac=0.02, one_sided_frac=0.3)), (202, dict(pad=3)),
+                                      (203, dict(n_frac=0.2))])
+def test_twobit_native_library_equals_byte_library(ramcu, oracle, seed, kw):
+    """flank feed: the library decoded on the device from the .2bit records' own packed DNA
+    (ramcu_library_from_twobit) is identical to the one packed from the reference loader's bytes
+    (ramcu_library_upload), and extends to the same result as the oracle"""
+    fam = synth.make_family(seed, 37, 211, 0.15, **kw)
+    blob, wins, ns, nl, total = synth.family_twobit_windows(fam)
+    assert total == fam.sequence.size
+    h2 = ramcu.library_from_twobit(blob, wins, ns, nl, total)
+    h1 = ramcu.upload_library(fam.sequence)
+    try:
+        a2, an = ramcu.download_library(h2, total)
+        b2, bn = ramcu.download_library(h1, total)
+        want = np.where(fam.sequence > 3, 99, fam.sequence)
+        assert np.array_equal(_decode_packed(b2, bn, total), want)
+        assert np.array_equal(_decode_packed(a2, an, total), want)
+        osc = oracle.scoring("14p43g")
+        p = make_params(bandwidth=40, minimprovement=30, L=20000)
+        for d in (1, 0):
+            ref = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+            got = _got(*ramcu.extend(h2, d, fam.cores, osc.to_product(), p))
+            support.compare_extend(ref, got, f"twobit library dir={d}")
+    finally:
+        ramcu.free_library(h1)
+        ramcu.free_library(h2)

@@ -136,3 +136,26 @@ def test_lpt_shard_partitions_every_family_once():
         assert flat == list(range(37))
         loads = [sum(costs[i] for i in s) for s in shards]
         assert max(loads) - min(loads) <= max(costs)
+
+
+def test_twobit_window_spec_matches_the_written_file(tmp_path):
+    """synth.family_twobit_windows (input of ramcu_library_from_twobit) describes exactly the packed
+    DNA that write_twobit puts into the .2bit records, and decodes back to the loader's bytes"""
+    fam = synth.make_family(7, 9, 57, 0.1, one_sided_frac=0.4, n_frac=0.05, pad=5)
+    blob, wins, ns, nl, total = synth.family_twobit_windows(fam)
+    assert total == fam.sequence.size and wins[:, 1].sum() == total
+    two2ram = np.array([3, 1, 0, 2], dtype=np.uint8)
+    out = np.zeros(total, dtype=np.uint8)
+    for dst, ln, sbyte, sbase in wins.tolist():
+        idx = sbase + np.arange(ln)
+        byte = blob[sbyte + (idx >> 2)]
+        out[dst:dst + ln] = two2ram[(byte >> (6 - 2 * (idx & 3))) & 3]
+    for a, b in zip(ns.tolist(), nl.tolist()):
+        out[a:a + b] = 99
+    assert np.array_equal(out, fam.sequence)
+    # the same packed bytes are what the .2bit file holds
+    p = str(tmp_path / "f.2bit")
+    synth.write_family_files(fam, p, str(tmp_path / "f.tsv"))
+    data = open(p, "rb").read()
+    rec0 = synth.pack_twobit_record(fam.seqs[0]).tobytes()
+    assert rec0 in data
