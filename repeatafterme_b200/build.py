@@ -97,10 +97,20 @@ def build_cli(force=False):
     return out
 
 
+def build_emulator():
+    """tests/emul/libramemul.so: the kernel source compiled for the CPU (test infrastructure; built
+    here so that a kernel edit that breaks the emulation shim shows up in the build check)"""
+    emul = os.path.join(ROOT, "tests", "emul")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-DRAMCU_EMUL", "-I.", "-fPIC", "-shared", "-pthread",
+                           "-o", "libramemul.so", "emul_driver.cpp"], cwd=emul)
+    return os.path.join(emul, "libramemul.so")
+
+
 def build_all(force=False):
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"])
     lib = build_libramcu(force=force)
     cli = build_cli(force=force)
+    build_emulator()
     return lib, cli
 
 
