@@ -147,13 +147,26 @@ __device__ __forceinline__ int fetch_code(const uint32_t *__restrict__ lib2,
   return ((nm >> ((int) p & 31)) & 1) ? 4 : c;
 }
 
+// byte j of a window register, zero-extended: one PRMT instead of shift + mask
+__device__ __forceinline__ int win_byte(const uint32_t w, const int j)
+{
+#ifdef RAMCU_EMUL
+  return (int) ((w >> (8 * j)) & 0xffu);
+#else
+  return (int) __byte_perm(w, 0u, 0x4440u | (unsigned) j);
+#endif
+}
+
 // One pass over the lane's C cells for NC candidates (NC = 4: all bases; NC = 1: base a0).
 //   SLOW   : per-cell bounds predicates (exact out-of-bounds / edge / dead-cell semantics)
 //   COMMIT : write the new row into Sp/Gp and track the first cell whose score == bestv
 //   BEST   : accumulate the row best per candidate
+//   PDOUT  : leave P = max(Sp,Gp) and D (the two candidate-independent terms of the row) in Sp/Gp
+//            in place of the previous row, which this pass has finished reading at that point
+//   PDIN   : Sp/Gp already hold P and D (the commit after a PDOUT sweep recomputes neither)
 // sin/gin  : S and G of the cell left of this lane's first cell (current row)
 // gout     : G of this lane's last cell
-template <int C, int G, int WS, bool SLOW, int NC, bool COMMIT, bool BEST>
+template <int C, int G, int WS, bool SLOW, int NC, bool COMMIT, bool BEST, bool PDIN, bool PDOUT>
 __device__ __forceinline__ void band_pass(int (&Sp)[C], int (&Gp)[C], const int SpN,
                                           const int GpN, const uint32_t *win, const char *lutb,
                                           const int a0, const int go, const int ge,
@@ -175,17 +188,28 @@ __device__ __forceinline__ void band_pass(int (&Sp)[C], int (&Gp)[C], const int 
     sprev[a] = sin[a];
     gprev[a] = gin[a];
   }
+  static_assert(!(PDIN && PDOUT) && !(PDOUT && COMMIT), "P/D hand-over is sweep -> commit");
   if (COMMIT)
     idx = kBig;
+  unsigned hits = 0;   // COMMIT, C <= 32: bit k set when cell k holds the row best
 
 #pragma unroll
   for (int k = 0; k < C; ++k)
   {
-    const int sN = (k + 1 < C) ? Sp[(k + 1 < C) ? k + 1 : 0] : SpN;
-    const int gN = (k + 1 < C) ? Gp[(k + 1 < C) ? k + 1 : 0] : GpN;
-    const int P = imax(Sp[k], Gp[k]);
-    int D = imax(sN + goe, gN + ge);
-    const int byte = (int) ((win[k >> 2] >> (8 * (k & 3))) & 0xffu);
+    int P, D;
+    if (PDIN)
+    {
+      P = Sp[k];
+      D = Gp[k];
+    }
+    else
+    {
+      const int sN = (k + 1 < C) ? Sp[(k + 1 < C) ? k + 1 : 0] : SpN;
+      const int gN = (k + 1 < C) ? Gp[(k + 1 < C) ? k + 1 : 0] : GpN;
+      P = imax(Sp[k], Gp[k]);
+      D = imax(sN + goe, gN + ge);
+    }
+    const int byte = win_byte(win[k >> 2], k & 3);
     bool real = true, inb = true;
     int E = 0;
     if (SLOW)
@@ -204,6 +228,11 @@ __device__ __forceinline__ void band_pass(int (&Sp)[C], int (&Gp)[C], const int 
         D = is_last ? kNeg : D;
       if (k > kR)
         real = !is_last;
+    }
+    if (PDOUT)
+    {
+      Sp[k] = P;
+      Gp[k] = D;
     }
     int mv[NC];
     if constexpr (NC == 4)
@@ -250,9 +279,17 @@ __device__ __forceinline__ void band_pass(int (&Sp)[C], int (&Gp)[C], const int 
       Sp[k] = s0;
       Gp[k] = g0;
       const bool hit = (imax(s0, g0) == bestv) && real;
-      idx = min(idx, hit ? k : kBig);
+      if constexpr (C <= 32)
+      {
+        if (hit)
+          hits |= 1u << k;
+      }
+      else
+        idx = min(idx, hit ? k : kBig);
     }
   }
+  if constexpr (COMMIT && C <= 32)
+    idx = hits ? (__ffs((int) hits) - 1) : kBig;
 #pragma unroll
   for (int a = 0; a < NC; ++a)
     gout[a] = gprev[a];
@@ -265,7 +302,7 @@ __device__ __forceinline__ void band_pass(int (&Sp)[C], int (&Gp)[C], const int 
 // tag (column + 1) has not arrived yet. The tag travels in the same word as the data, so no fence
 // is needed and one L2 round trip suffices once the last CTA has published. Slots are double
 // buffered by column parity: a CTA overwrites a slot two columns later, after everyone read it.
-constexpr int kGatherU = 5;
+constexpr int kGatherU = 2;   // 64 slots per round covers the <= kSlotMaxCtas CTAs of this path
 
 __device__ __forceinline__ void ld_slot(const unsigned long long *p, unsigned long long (&w)[4])
 {
@@ -478,7 +515,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       }
       // S of this lane's last cell for the four candidates -> left input of the next lane
       {
-        const int byte = (int) ((win[(C - 1) >> 2] >> (8 * ((C - 1) & 3))) & 0xffu);
+        const int byte = win_byte(win[(C - 1) >> 2], (C - 1) & 3);
         const int4 m4 = *reinterpret_cast<const int4 *>(lutb + byte);
         const int P = imax(Sp[C - 1], Gp[C - 1]);
         int sl[4] = {P + m4.x, P + m4.y, P + m4.z, P + m4.w};
@@ -508,7 +545,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       }
       if (fast)
       {
-        band_pass<C, G, WS, false, 4, false, true>(Sp, Gp, SpN, GpN, win, lutb, 0, go, ge, sin4,
+        band_pass<C, G, WS, false, 4, false, true, false, true>(Sp, Gp, SpN, GpN, win, lutb, 0, go, ge, sin4,
                                                    gin, agg, best, 0, idx_dummy, gl, W, B, r,
                                                    tmin, tmax);
 #pragma unroll
@@ -533,7 +570,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       else
       {
         int nobest[4] = {0, 0, 0, 0};
-        band_pass<C, G, WS, true, 4, false, false>(Sp, Gp, SpN, GpN, win, lutb, 0, go, ge, sin4,
+        band_pass<C, G, WS, true, 4, false, false, false, false>(Sp, Gp, SpN, GpN, win, lutb, 0, go, ge, sin4,
                                                    gin, agg, nobest, 0, idx_dummy, gl, W, B, r,
                                                    tmin, tmax);
         // (aggregate, transfer) scan: an out-of-bounds cell anywhere in a lane blocks the carry
@@ -560,7 +597,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
           gin2[a] = (gl == 0) ? (kNeg - ge) : carry[a];
         }
         int agg2[4];
-        band_pass<C, G, WS, true, 4, false, true>(Sp, Gp, SpN, GpN, win, lutb, 0, go, ge, sin4,
+        band_pass<C, G, WS, true, 4, false, true, false, true>(Sp, Gp, SpN, GpN, win, lutb, 0, go, ge, sin4,
                                                   gin2, agg2, best, 0, idx_dummy, gl, W, B, r,
                                                   tmin, tmax);
       }
@@ -657,11 +694,11 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       int gout1[1], nob[1] = {0};
       int idx = kBig;
       if (fast)
-        band_pass<C, G, WS, false, 1, true, false>(Sp, Gp, SpN, GpN, win, lutb, besta, go, ge, cs,
+        band_pass<C, G, WS, false, 1, true, false, true, false>(Sp, Gp, SpN, GpN, win, lutb, besta, go, ge, cs,
                                                    cg, gout1, nob, bestb, idx, gl, W, B, r, tmin,
                                                    tmax);
       else
-        band_pass<C, G, WS, true, 1, true, false>(Sp, Gp, SpN, GpN, win, lutb, besta, go, ge, cs,
+        band_pass<C, G, WS, true, 1, true, false, true, false>(Sp, Gp, SpN, GpN, win, lutb, besta, go, ge, cs,
                                                   cg, gout1, nob, bestb, idx, gl, W, B, r, tmin,
                                                   tmax);
       int kidx = (idx < kBig) ? gl * C + idx : kBig;

@@ -91,6 +91,7 @@ static inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); 
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __sync_fetch_and_or(p, v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __sync_fetch_and_add(p, v); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s)
 {
   const unsigned long long v = ((unsigned long long) hi << 32) | lo;
