@@ -84,7 +84,8 @@ typedef struct
   int32_t lanes_per_instance; /* 0 = auto; else force 1,2,4,8,16,32 (tuning/tests)            */
   int32_t concurrent_instances; /* hint: instances of OTHER families expected to share the GPU
                                  * with this one (ramcu_batch_run); 0 = runs alone            */
-  int32_t reserved[1];
+  int32_t cta_thread_limit;   /* 0 = auto; else only tilings compiled for this CTA limit, i.e.
+                               * 65536 / limit registers per thread (tuning/tests)              */
 } ramcu_params_t;
 
 typedef struct
@@ -172,6 +173,25 @@ int ramcu_job_free(ramcu_ctx *ctx, ramcu_job *job);
 
 /* Enqueue many independent jobs (families) so that they share the GPU concurrently. */
 int ramcu_batch_run(ramcu_ctx *ctx, int n_jobs, ramcu_job **jobs);
+
+/* Both passes of one family in one launch. Replaces the two extend_alignment() calls of main()
+ * (ram_extend.c:424-427 right, :506-509 left) WHEN the overlap-avoidance step between them
+ * (ram_extend.c:445-499) leaves every lower/upperSeqBound unchanged: both passes then read the
+ * same `cores`. The caller owns that check (csrc/ramx_boundary.c compares the bounds main() hands
+ * to the left pass with the ones used here and re-runs the left pass if any differs).
+ * CTAs of the two passes share the SMs, so one pass computes while the other waits for its
+ * per-column exchange; results are bit-identical to two ramcu_extend() calls on the same cores.
+ * If the two passes cannot be co-resident they run one after the other.
+ * ramcu_job_create_pair + ramcu_batch_run(ctx, 2, {right, left}) + ramcu_job_fetch is the split
+ * form; kernel_ms of either result is the device time of the whole pair. */
+int ramcu_job_create_pair(ramcu_ctx *ctx, ramcu_library *lib, int n_cores, const ramcu_core_t *cores,
+                          const ramcu_scoring_t *scoring, const ramcu_params_t *params,
+                          ramcu_job **right, ramcu_job **left);
+int ramcu_extend_pair(ramcu_ctx *ctx, ramcu_library *lib, int n_cores, const ramcu_core_t *cores,
+                      const ramcu_scoring_t *scoring, const ramcu_params_t *params,
+                      uint8_t *master_right, int32_t *ext_len_right, int32_t *score_add_right,
+                      ramcu_result_t *res_right, uint8_t *master_left, int32_t *ext_len_left,
+                      int32_t *score_add_left, ramcu_result_t *res_left);
 
 /* Test-only second boundary (compute_nw_row, bnw_extend.h:52-58). Runs the extension kernel for
  * `n_rows` rows with the consensus FORCED to forced_cons[r] (NULL = argmax as usual) and returns

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libramcu.so")
+LIB_PATH = os.environ.get("RAMCU_LIB") or os.path.join(HERE, "csrc", "libramcu.so")   # RAMCU_LIB: kernel experiments
 
 #: struct coreAlignment (reference common.h:80-98) flattened == ramcu_core_t
 CORE_DTYPE = np.dtype(
@@ -36,6 +36,7 @@ ABI_SYMBOLS = (
     "ramcu_device_info", "ramcu_int32_peak", "ramcu_scoring_by_name", "ramcu_library_upload",
     "ramcu_library_from_device", "ramcu_library_from_twobit", "ramcu_library_download", "ramcu_library_free", "ramcu_extend", "ramcu_job_create",
     "ramcu_job_run", "ramcu_job_fetch", "ramcu_job_free", "ramcu_batch_run", "ramcu_debug_rows",
+    "ramcu_job_create_pair", "ramcu_extend_pair",
 )
 
 
@@ -69,7 +70,7 @@ class Params(C.Structure):
         ("when_to_stop", C.c_int32),
         ("lanes_per_instance", C.c_int32),
         ("concurrent_instances", C.c_int32),
-        ("reserved", C.c_int32 * 1),
+        ("cta_thread_limit", C.c_int32),
     ]
 
 
@@ -92,12 +93,13 @@ class ExtendResult(C.Structure):
 
 
 def make_params(bandwidth=14, cappenalty=-90, minimprovement=27, L=10000, when_to_stop=100,
-                lanes_per_instance=0, concurrent_instances=0) -> Params:
+                lanes_per_instance=0, concurrent_instances=0, cta_thread_limit=0) -> Params:
     """Defaults are those of the RAMExtend CLI (ram_extend.c:246-249, 301-344)."""
     p = Params()
     p.bandwidth, p.cappenalty, p.minimprovement, p.L, p.when_to_stop, p.lanes_per_instance = (
         bandwidth, cappenalty, minimprovement, L, when_to_stop, lanes_per_instance)
     p.concurrent_instances = concurrent_instances
+    p.cta_thread_limit = cta_thread_limit
     return p
 
 
@@ -135,6 +137,9 @@ def load_ramcu(path: str = LIB_PATH) -> C.CDLL:
     lib.ramcu_job_fetch.argtypes = [vp, vp, vp, vp, vp, P(ExtendResult)]
     lib.ramcu_job_free.argtypes = [vp, vp]
     lib.ramcu_batch_run.argtypes = [vp, i32, P(vp)]
+    lib.ramcu_job_create_pair.argtypes = [vp, vp, i32, vp, P(Scoring), P(Params), P(vp), P(vp)]
+    lib.ramcu_extend_pair.argtypes = [vp, vp, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult),
+                                      vp, vp, vp, P(ExtendResult)]
     lib.ramcu_debug_rows.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), i32, vp, vp, vp, vp]
     for name in ABI_SYMBOLS:
         if name not in ("ramcu_last_error", "ramcu_destroy"):
@@ -248,6 +253,26 @@ class RamCu:
         self._check(self.lib.ramcu_job_create(self.ctx, lib_h, direction, cores.size, cores.ctypes.data,
                                               C.byref(scoring), C.byref(params), C.byref(h)))
         return h
+
+    def job_create_pair(self, lib_h, cores: np.ndarray, scoring: Scoring, params: Params):
+        """Right and left pass of one family laid out to share one launch (ramcu_job_create_pair);
+        run them with batch_run([right, left])."""
+        cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+        r, l = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.ramcu_job_create_pair(self.ctx, lib_h, cores.size, cores.ctypes.data,
+                                                   C.byref(scoring), C.byref(params), C.byref(r), C.byref(l)))
+        return r, l
+
+    def extend_pair(self, lib_h, cores: np.ndarray, scoring: Scoring, params: Params):
+        """Both extend_alignment() calls of main() in one launch; valid as the left pass only when the
+        overlap-avoidance step between them changes no bound (include/ramcu.h)."""
+        jobs = self.job_create_pair(lib_h, cores, scoring, params)
+        try:
+            self.batch_run(list(jobs))
+            return [self.job_fetch(j, cores.size, params.L) for j in jobs]
+        finally:
+            for j in jobs:
+                self.job_free(j)
 
     def job_run(self, job):
         self._check(self.lib.ramcu_job_run(self.ctx, job))

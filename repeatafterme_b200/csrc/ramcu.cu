@@ -48,7 +48,13 @@ static int fail(int code, const char *fmt, ...)
 // ------------------------------------------------------------------------------------------
 // kernel registry: band tilings
 // ------------------------------------------------------------------------------------------
-static const int kBatchThreads = 128;   // CTA size used when many families share a launch
+static int batch_threads_init()
+{
+  const char *e = getenv("RAMCU_BATCH_THREADS");   // tuning aid
+  const int v = e ? atoi(e) : 0;
+  return (v >= 32 && v <= 1024 && v % 32 == 0) ? v : 128;
+}
+static const int kBatchThreads = batch_threads_init();   // CTA size used when many families share a launch
 
 // how a family is laid out on the grid
 struct Plan
@@ -516,7 +522,7 @@ static double solo_cost(const ramcu_ctx *c, const KernelCfg *k, int n_ext, const
 }
 
 static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force_G,
-                                 int concurrent_instances, Plan *solo, int *batch_ctas)
+                                 int concurrent_instances, int force_maxt, Plan *solo, int *batch_ctas)
 {
   const int W = 2 * B + 1;
   std::vector<const KernelCfg *> cand;
@@ -539,9 +545,14 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force
   const KernelCfg *best = nullptr;
   double best_cost = 0;
   const bool crowded = concurrent_instances >= c->sm_count * 128;
+  bool have_maxt = false;   // cta_thread_limit is a preference: ignored when no tiling of this band has it
+  for (const KernelCfg *k : cand)
+    have_maxt = have_maxt || (k->maxt == force_maxt && (force_G <= 0 || k->G == force_G));
   for (const KernelCfg *k : cand)
   {
     if (force_G > 0 && k->G != force_G)
+      continue;
+    if (force_maxt > 0 && k->maxt != force_maxt && have_maxt)
       continue;
     Plan p;
     int nb = 0;
@@ -625,7 +636,7 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
   j->n_ctas = 0;
   if (j->n_ext > 0 && pr->L > 0)
   {
-    j->cfg = pick_cfg(c, B, j->n_ext, pr->lanes_per_instance, pr->concurrent_instances, &j->solo,
+    j->cfg = pick_cfg(c, B, j->n_ext, pr->lanes_per_instance, pr->concurrent_instances, pr->cta_thread_limit, &j->solo,
                       &j->batch_ctas);
     if (!j->cfg)
     {
@@ -902,6 +913,94 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
   for (int i = 0; i < n_jobs; ++i)
     jobs[i]->timed = true;
   return RAMCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// both passes of one family in one launch
+// ------------------------------------------------------------------------------------------
+// main() extends right, narrows the bounds of cores that a right extension ran into
+// (ram_extend.c:445-499), then extends left with those bounds. When that step leaves every bound
+// as it was (the caller checks: ramx_boundary.c compares the bounds it is handed for the left
+// pass with the ones used here), the two passes are independent column loops over the same
+// cores. Running them as two families of one launch puts CTAs of both on every SM, so one pass
+// computes while the other waits for its per-column grid exchange.
+extern "C" int ramcu_job_create_pair(ramcu_ctx *c, ramcu_library *lib, int n_cores,
+                                     const ramcu_core_t *cores, const ramcu_scoring_t *sc,
+                                     const ramcu_params_t *pr, ramcu_job **right, ramcu_job **left)
+{
+  if (!c || !pr || !right || !left || (n_cores > 0 && !cores))
+    return fail(RAMCU_ERR_ARG, "ramcu_job_create_pair: NULL argument");
+  *right = *left = nullptr;
+  int n_r = 0, n_l = 0;
+  for (int i = 0; i < n_cores; ++i)
+  {
+    n_r += cores[i].right_extendable ? 1 : 0;
+    n_l += cores[i].left_extendable ? 1 : 0;
+  }
+  ramcu_params_t p = *pr;
+  bool together = false;
+  if (n_r > 0 && n_l > 0 && pr->L > 0 && pr->bandwidth >= 0 && pr->bandwidth <= RAMCU_MAX_BANDWIDTH)
+  {
+    CK(cudaSetDevice(c->device));
+    Plan solo;
+    int nb = 0;
+    const KernelCfg *k0 = pick_cfg(c, pr->bandwidth, std::max(n_r, n_l), pr->lanes_per_instance,
+                                   pr->concurrent_instances, pr->cta_thread_limit, &solo, &nb);
+    if (k0)
+    {
+      // same lanes per instance as the family alone; full registers if both passes fit the
+      // device side by side, else the tiling compiled for half the registers
+      const int tries[2] = {k0->maxt, 512};
+      for (int t = 0; t < 2 && !together; ++t)
+      {
+        if (pr->cta_thread_limit > 0 && tries[t] != pr->cta_thread_limit)
+          continue;
+        Plan sr, sl;
+        int br = 0, bl = 0;
+        const KernelCfg *kr = pick_cfg(c, pr->bandwidth, n_r, k0->G, pr->concurrent_instances, tries[t], &sr, &br);
+        const KernelCfg *kl = pick_cfg(c, pr->bandwidth, n_l, k0->G, pr->concurrent_instances, tries[t], &sl, &bl);
+        if (!kr || kr != kl || kr->maxt != tries[t] || br <= 0 || bl <= 0)
+          continue;
+        if ((long long) br + bl > (long long) ctas_per_sm(kr, kBatchThreads) * c->sm_count)
+          continue;
+        p.lanes_per_instance = k0->G;
+        p.cta_thread_limit = tries[t];
+        together = true;
+      }
+    }
+  }
+  int rc = job_create_impl(c, lib, 1, n_cores, cores, sc, &p, 0, nullptr, right);
+  if (!rc)
+    rc = job_create_impl(c, lib, 0, n_cores, cores, sc, &p, 0, nullptr, left);
+  if (rc)
+  {
+    ramcu_job_free(c, *right);
+    *right = nullptr;
+    return rc;
+  }
+  if (!together)   // ramcu_batch_run then launches each pass on its own, one after the other
+    (*right)->batch_ctas = (*left)->batch_ctas = 0;
+  return RAMCU_OK;
+}
+
+extern "C" int ramcu_extend_pair(ramcu_ctx *c, ramcu_library *lib, int n_cores, const ramcu_core_t *cores,
+                                 const ramcu_scoring_t *sc, const ramcu_params_t *pr,
+                                 uint8_t *master_right, int32_t *ext_len_right, int32_t *score_add_right,
+                                 ramcu_result_t *res_right, uint8_t *master_left, int32_t *ext_len_left,
+                                 int32_t *score_add_left, ramcu_result_t *res_left)
+{
+  ramcu_job *jobs[2] = {nullptr, nullptr};
+  int rc = ramcu_job_create_pair(c, lib, n_cores, cores, sc, pr, &jobs[0], &jobs[1]);
+  if (rc)
+    return rc;
+  rc = ramcu_batch_run(c, 2, jobs);
+  if (!rc)
+    rc = ramcu_job_fetch(c, jobs[0], master_right, ext_len_right, score_add_right, res_right);
+  if (!rc)
+    rc = ramcu_job_fetch(c, jobs[1], master_left, ext_len_left, score_add_left, res_left);
+  ramcu_job_free(c, jobs[0]);
+  ramcu_job_free(c, jobs[1]);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------

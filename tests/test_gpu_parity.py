@@ -158,6 +158,79 @@ def test_batch_equals_individual_runs(ramcu, oracle):
             support.compare_extend(want, got, f"batch dir={d}")
 
 
+@pytest.mark.parametrize("seed,n,flank,B,matrix,kw", [
+    (111, 300, 300, 40, "14p43g", dict(one_sided_frac=0.2, n_frac=0.005)),   # both passes in few CTAs
+    (112, 90, 250, 14, "20p43g", dict()),                                    # one CTA per pass
+    (113, 2500, 150, 40, "14p43g", dict(one_sided_frac=0.1)),                # many CTAs, full registers
+    (114, 400, 200, 100, "25p43g", dict(pad=3)),
+    (115, 500, 200, 33, "18p43g", dict()),                                   # runtime-width tiling
+])
+def test_pair_launch_vs_oracle(ramcu, oracle, seed, n, flank, B, matrix, kw):
+    """ramcu_extend_pair (right and left pass of one family sharing one launch) == oracle ==
+    two separate ramcu_extend calls, including families with one-side-extendable cores"""
+    fam = synth.make_family(seed, n, flank, 0.15, **kw)
+    osc = oracle.scoring(matrix)
+    lib = ramcu.upload_library(fam.sequence)
+    try:
+        p = make_params(bandwidth=B, minimprovement=27, L=20000)
+        pair = [_got(*o) for o in ramcu.extend_pair(lib, fam.cores, osc.to_product(), p)]
+        for d, got in zip((1, 0), pair):
+            want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+            support.compare_extend(want, got, f"pair seed={seed} dir={d}")
+            alone = _got(*ramcu.extend(lib, d, fam.cores, osc.to_product(), p))
+            support.compare_extend(alone, got, f"pair vs alone seed={seed} dir={d}")
+    finally:
+        ramcu.free_library(lib)
+
+
+def test_pair_launch_edge_cases(ramcu, oracle):
+    """nothing extendable on one side / on both sides / empty family through the pair entry"""
+    fam = synth.make_family(121, 60, 200, 0.15)
+    osc = oracle.scoring("14p43g")
+    p = make_params(bandwidth=40, minimprovement=30, L=20000)
+    lib = ramcu.upload_library(fam.sequence)
+    try:
+        for mask in ((1, 0), (0, 1), (0, 0)):
+            cores = fam.cores.copy()
+            cores["right_extendable"] = mask[0]
+            cores["left_extendable"] = mask[1]
+            pair = [_got(*o) for o in ramcu.extend_pair(lib, cores, osc.to_product(), p)]
+            for d, got in zip((1, 0), pair):
+                want = oracle.extend(d, cores, fam.sequence, osc, p)
+                support.compare_extend(want, got, f"pair mask={mask} dir={d}")
+        empty = [_got(*o) for o in ramcu.extend_pair(lib, fam.cores[:0], osc.to_product(), p)]
+        assert [e["extended_bp"] for e in empty] == [0, 0]
+    finally:
+        ramcu.free_library(lib)
+
+
+def test_low_register_tilings_vs_oracle(ramcu, oracle):
+    """the tilings compiled for half the registers (cta_thread_limit=512: the capacity route of the
+    pair launch) against the oracle for every bandwidth that has them"""
+    ran = 0
+    for seed, B, matrix in ((131, 14, "20p43g"), (132, 20, "18p43g"), (133, 40, "14p43g"), (134, 60, "14p43g"),
+                            (135, 80, "25p43g"), (136, 100, "18p43g")):
+        fam = synth.make_family(seed, 120, 220, 0.15, one_sided_frac=0.1)
+        osc = oracle.scoring(matrix)
+        lib = ramcu.upload_library(fam.sequence)
+        try:
+            base = make_params(bandwidth=B, minimprovement=27, L=20000)
+            want = [oracle.extend(d, fam.cores, fam.sequence, osc, base) for d in (1, 0)]
+            for G in range(1, 9):
+                p = make_params(bandwidth=B, minimprovement=27, L=20000, lanes_per_instance=G, cta_thread_limit=512)
+                try:
+                    pair = [_got(*o) for o in ramcu.extend_pair(lib, fam.cores, osc.to_product(), p)]
+                except RamCuError as ex:
+                    assert "no band tiling" in str(ex), ex
+                    continue
+                for w, got in zip(want, pair):
+                    support.compare_extend(w, got, f"B={B} G={G} limit=512")
+                ran += 1
+        finally:
+            ramcu.free_library(lib)
+    assert ran >= 12
+
+
 def test_full_size_properties(ramcu):
     """BASELINE config 4 scale (10k instances is too slow for the oracle): independent band
     tilings must agree bit for bit, instance order must not matter, and mirroring the library
@@ -174,6 +247,10 @@ def test_full_size_properties(ramcu):
             for a, b in zip(outs[1], outs[G]):
                 support.compare_extend(a, b, f"G=1 vs G={G}")
         assert outs[1][0]["extended_bp"] > 1000 and outs[1][1]["extended_bp"] > 1000
+        # both passes in one launch (20 000 instance-bands: only the half-register tiling fits)
+        pair = [_got(*o) for o in ramcu.extend_pair(lib, fam.cores, sc, make_params(bandwidth=40, minimprovement=30, L=20000))]
+        for a, b in zip(outs[1], pair):
+            support.compare_extend(a, b, "separate passes vs pair launch")
         # permutation invariance
         perm = np.random.default_rng(0).permutation(fam.cores.size)
         p = make_params(bandwidth=40, minimprovement=30, L=20000)

@@ -13,20 +13,20 @@ pick = np.random.default_rng(0).choice(len(specs), size=nf, replace=False)
 fams = [synth.family_from_spec(specs[i]) for i in sorted(pick)]
 libs = [rc.upload_library(f.sequence) for f in fams]
 total = sum(f.n for f in fams)
-def run(policy):
+def run(policy, maxt=0):
     jobs = []
     for f, h in zip(fams, libs):
         p = dict(f.params); m = p.pop("matrix")
         if policy == "auto":
             p["concurrent_instances"] = total - f.n
-            j = rc.job_create(h, 1, f.cores, rc.scoring(m), make_params(**p))
+            j = rc.job_create(h, 1, f.cores, rc.scoring(m), make_params(cta_thread_limit=maxt, **p))
         elif policy == "solo":
             j = rc.job_create(h, 1, f.cores, rc.scoring(m), make_params(**p))
         else:
             j = None
             for G in policy:
                 try:
-                    j = rc.job_create(h, 1, f.cores, rc.scoring(m), make_params(lanes_per_instance=G, **p)); break
+                    j = rc.job_create(h, 1, f.cores, rc.scoring(m), make_params(lanes_per_instance=G, cta_thread_limit=maxt, **p)); break
                 except RamCuError:
                     continue
             if j is None:
@@ -39,6 +39,7 @@ def run(policy):
     cu = sum(o[0].rows_processed * o[0].n_extendable * (2 * f.params["bandwidth"] + 1) * 4.0 for o, f in zip(outs, fams))
     gs = [o[0].lanes_per_instance for o in outs]
     for j in jobs: rc.job_free(j)
-    print(json.dumps(dict(policy=str(policy), ms=round(best * 1e3, 1), gcups=round(cu / best / 1e9, 1), G=gs)), flush=True)
-for pol in ("auto", "solo", (2, 3, 4, 5, 8), (3, 4, 5, 2, 8), (4, 5, 3, 6, 8, 2), (8, 6, 5, 4, 16, 3)):
-    run(pol)
+    print(json.dumps(dict(policy=str(policy), maxt=maxt, ms=round(best * 1e3, 1), gcups=round(cu / best / 1e9, 1), G=gs)), flush=True)
+for pol in ("auto", "solo", (2, 3, 4, 5, 8), (3, 4, 5, 2, 8), (4, 5, 3, 6, 8, 2)):
+    for maxt in (0, 512):
+        run(pol, maxt)
