@@ -56,8 +56,8 @@ def _as_dict(res, master, ext_len, score_add, bandwidth):
 
 def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
     """Extend a list of families (objects with .sequence, .cores, .params as in synth.Family).
-    Host buffers in, host results out: library upload, right pass of every family as one batch,
-    fetch, left pass of every family as one batch, fetch."""
+    Host buffers in, host results out: library upload, every pass of every family as one batch
+    (or right batch, `between_passes` hook, left batch), fetch."""
     libs, scs, prs = [], [], []
     total = sum(int(f.cores.size) for f in fams)
     for f in fams:
@@ -72,20 +72,24 @@ def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
         libs.append(rc.upload_library(f.sequence))
     results = [FamilyResult() for _ in fams]
     try:
-        for direction in (1, 0):
-            jobs = [rc.job_create(libs[i], direction, f.cores, scs[i], prs[i]) for i, f in enumerate(fams)]
+        # Without a between-passes step (the overlap avoidance of ram_extend.c:445-499 belongs to the
+        # caller) the left passes do not depend on the right ones: all 2 x len(fams) column loops go
+        # into one batch and share the SMs. With one, right batch -> hook -> left batch.
+        rounds = [(1, 0)] if between_passes is None else [(1,), (0,)]
+        for dirs in rounds:
+            jobs = [(i, d, rc.job_create(libs[i], d, f.cores, scs[i], prs[i])) for d in dirs for i, f in enumerate(fams)]
             if len(jobs) == 1:
-                rc.job_run(jobs[0])
+                rc.job_run(jobs[0][2])
             else:
-                rc.batch_run(jobs)
-            for i, f in enumerate(fams):
-                out = _as_dict(*rc.job_fetch(jobs[i], f.cores.size, prs[i].L), prs[i].bandwidth)
-                if direction:
+                rc.batch_run([j for _, _, j in jobs])
+            for i, d, j in jobs:
+                out = _as_dict(*rc.job_fetch(j, fams[i].cores.size, prs[i].L), prs[i].bandwidth)
+                if d:
                     results[i].right = out
                 else:
                     results[i].left = out
-                rc.job_free(jobs[i])
-            if direction and between_passes is not None:
+                rc.job_free(j)
+            if dirs == (1,):
                 for i, f in enumerate(fams):
                     between_passes(f, results[i].right)
     finally:

@@ -16,6 +16,14 @@
  * to the 4x5 table the path reads, the VERBOSE<=3 prints of ram_extend.c:886-892,1218-1231, and
  * the write-back of master[] / per-core fields (ram_extend.c:1092-1095,1234-1247). No DP.
  * There is no CPU fallback: a CUDA failure prints the error and exits, in the reference's style.
+ *
+ * Pair launch: main() calls right, narrows the bounds of cores a right extension ran into
+ * (ram_extend.c:445-499), then calls left. The right call here runs BOTH passes in one launch
+ * (ramcu_extend_pair: the passes hide each other's per-column exchange) with the bounds as they
+ * are then, and keeps the left results together with the flattened cores they were computed
+ * from. The left call flattens the cores again; if they are byte-identical (no bound was
+ * narrowed) and nothing else changed, the kept results ARE the left pass; otherwise the left
+ * pass is run again on its own. RAMCU_PAIR=0 disables this (two launches, as before).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -38,6 +46,29 @@ static ramcu_ctx *g_ctx = NULL;
 static ramcu_library *g_lib = NULL;
 static const char *g_lib_seq = NULL;
 static uint64_t g_lib_len = 0;
+
+/* left-pass results computed ahead by the right call, and what they were computed from */
+static struct
+{
+  int valid, n, L;
+  ramcu_core_t *cores;
+  ramcu_scoring_t sc;
+  ramcu_params_t pr;
+  const ramcu_library *lib;
+  uint8_t *cons;
+  int32_t *ext_len, *score_add;
+  ramcu_result_t res;
+} g_ahead;
+
+static void
+ahead_drop(void)
+{
+  free(g_ahead.cores);
+  free(g_ahead.cons);
+  free(g_ahead.ext_len);
+  free(g_ahead.score_add);
+  memset(&g_ahead, 0, sizeof(g_ahead));
+}
 
 static void
 die(const char *what)
@@ -86,6 +117,7 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
   /* the right and the left pass share one library upload */
   if (g_lib == NULL || g_lib_seq != seqLib->sequence || g_lib_len != seqLib->length)
   {
+    ahead_drop();
     if (g_lib)
       ramcu_library_free(g_ctx, g_lib);
     if (ramcu_library_upload(g_ctx, (const uint8_t *) seqLib->sequence, seqLib->length, &g_lib) !=
@@ -138,9 +170,52 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
   pr.L = L;
   pr.when_to_stop = WHEN_TO_STOP;
 
-  if (ramcu_extend(g_ctx, g_lib, direction ? 1 : 0, n, cores, &sc, &pr, cons, ext_len, score_add,
-                   &res) != RAMCU_OK)
-    die("ramcu_extend");
+  {
+    const char *pe = getenv("RAMCU_PAIR");
+    const int pair_ok = !(pe && atoi(pe) == 0);
+    if (direction && pair_ok)
+    {
+      /* both passes now; the left results wait for the left call */
+      ahead_drop();
+      g_ahead.cores = (ramcu_core_t *) malloc((n > 0 ? n : 1) * sizeof(ramcu_core_t));
+      g_ahead.cons = (uint8_t *) malloc(L > 0 ? L : 1);
+      g_ahead.ext_len = (int32_t *) calloc(n > 0 ? n : 1, sizeof(int32_t));
+      g_ahead.score_add = (int32_t *) calloc(n > 0 ? n : 1, sizeof(int32_t));
+      if (!g_ahead.cores || !g_ahead.cons || !g_ahead.ext_len || !g_ahead.score_add)
+      {
+        printf("extend_alignment: Error could not allocate memory for the left-pass results\n");
+        exit(1);
+      }
+      if (ramcu_extend_pair(g_ctx, g_lib, n, cores, &sc, &pr, cons, ext_len, score_add, &res,
+                            g_ahead.cons, g_ahead.ext_len, g_ahead.score_add, &g_ahead.res) != RAMCU_OK)
+        die("ramcu_extend_pair");
+      memcpy(g_ahead.cores, cores, (size_t) n * sizeof(ramcu_core_t));
+      g_ahead.n = n;
+      g_ahead.L = L;
+      g_ahead.sc = sc;
+      g_ahead.pr = pr;
+      g_ahead.lib = g_lib;
+      g_ahead.valid = 1;
+    }
+    else if (!direction && g_ahead.valid && g_ahead.n == n && g_ahead.L == L && g_ahead.lib == g_lib &&
+             memcmp(&g_ahead.sc, &sc, sizeof(sc)) == 0 && memcmp(&g_ahead.pr, &pr, sizeof(pr)) == 0 &&
+             memcmp(g_ahead.cores, cores, (size_t) n * sizeof(ramcu_core_t)) == 0)
+    {
+      /* overlap avoidance changed nothing: the left pass has been computed already */
+      memcpy(cons, g_ahead.cons, L > 0 ? L : 1);
+      memcpy(ext_len, g_ahead.ext_len, (size_t) n * sizeof(int32_t));
+      memcpy(score_add, g_ahead.score_add, (size_t) n * sizeof(int32_t));
+      res = g_ahead.res;
+      ahead_drop();
+    }
+    else
+    {
+      ahead_drop();
+      if (ramcu_extend(g_ctx, g_lib, direction ? 1 : 0, n, cores, &sc, &pr, cons, ext_len, score_add,
+                       &res) != RAMCU_OK)
+        die("ramcu_extend");
+    }
+  }
 
   /* consensus of every processed row (ram_extend.c:1092-1095) */
   for (r = 0; r < res.rows_processed; r++)

@@ -41,7 +41,7 @@ DEF = dict(bandwidth=14, minimprovement=27, cappenalty=-90, L=10000, when_to_sto
 FLAT_CASES = ["config1_default", "config1_stk", "config1_b100", "synth_small", "l_limited", "ends",
               "satellite", "repeatscout", "wide25", "gapoverride", "ragged", "identical", "n_heavy",
               "b20", "b60"]
-CLI_CASES = ["config1_default", "config1_stk", "satellite", "synth", "tandem"]
+CLI_CASES = ["config1_default", "config1_stk", "satellite", "synth", "tandem", "overlap"]
 
 
 def satellite_inputs(seed=123456789):
@@ -81,6 +81,35 @@ def tandem_inputs(seed=77):
         parts.append(rng.integers(0, 4, 200, dtype=np.uint8))
         names.append(f"chr{s}")
         seqs.append(np.concatenate(parts))
+    return names, seqs, bed
+
+
+def overlap_inputs(seed=2):
+    """Right extensions that run into the left window of the next core on the same sequence, so that
+    OVERLAP AVOIDANCE (ram_extend.c:445-499) narrows bounds between the passes: core A (right-
+    extendable only) is followed by core B (left-extendable only); the loader gives both the whole
+    gap (sequence.c:625-743), A's extension crosses it, and B's lower bound moves before the left
+    pass. Six more sequences carry an unaffected B, so the left pass still extends."""
+    rng = np.random.default_rng(seed)
+    unit = rng.integers(0, 4, 500, dtype=np.uint8)
+    names, seqs, bed = [], [], []
+    for s in range(12):
+        b = synth.mutate(rng, unit, 0.05)
+        pre = rng.integers(0, 4, 250, dtype=np.uint8)
+        post = rng.integers(0, 4, 250, dtype=np.uint8)
+        if s < 6:
+            a = synth.mutate(rng, unit, 0.05)
+            gap = rng.integers(0, 4, 30, dtype=np.uint8)
+            seq = np.concatenate([pre, a, gap, b, post])
+            ca = pre.size + 100
+            bed.append((f"c{s}", ca, ca + 12, 0, 1, "+"))
+            cb = pre.size + a.size + gap.size + 300
+        else:
+            seq = np.concatenate([pre, b, post])
+            cb = pre.size + 300
+        bed.append((f"c{s}", cb, cb + 12, 1, 0, "+"))
+        names.append(f"c{s}")
+        seqs.append(seq)
     return names, seqs, bed
 
 
@@ -181,6 +210,9 @@ def build_cli_case(name):
         return dict(names=f.names, seqs=f.seqs, bed=f.bed, flags=list(STK_FLAGS))
     if name == "tandem":
         names, seqs, bed = tandem_inputs()
+        return dict(names=names, seqs=seqs, bed=bed, flags=["-bandwidth", "20", "-matrix", "18p43g", "-vvv"])
+    if name == "overlap":
+        names, seqs, bed = overlap_inputs()
         return dict(names=names, seqs=seqs, bed=bed, flags=["-bandwidth", "20", "-matrix", "18p43g", "-vvv"])
     raise KeyError(name)
 

@@ -34,6 +34,11 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "RAMExtend")
 
 
 def main():
+    only = sys.argv[1:]   # e.g. "cli_overlap": regenerate just that CLI case
+    if only:
+        global FLAT_CASES, CLI_CASES
+        FLAT_CASES = [c for c in FLAT_CASES if f"flat_{c}" in only]
+        CLI_CASES = [c for c in CLI_CASES if f"cli_{c}" in only]
     ref = support.Reference.try_load()
     assert ref is not None, "build oracle/_ref first (make -C oracle ref)"
 
@@ -64,7 +69,8 @@ def main():
     u["reference_rows"] = rows
     assert rows["right"][0][6]["gap"] == u["final_right_gap"]
     assert rows["right"][0][6]["sub"] == u["final_right_sub"]
-    json.dump(u, open(os.path.join(HERE, "unit_vectors.json"), "w"))
+    if not only:
+        json.dump(u, open(os.path.join(HERE, "unit_vectors.json"), "w"))
 
     # ---- flat cases -----------------------------------------------------------------------
     for name in FLAT_CASES:
@@ -111,7 +117,7 @@ def main():
         print("cli", name, m)
 
     # ---- ce10 families (configs 2-3) -------------------------------------------------------
-    for fam in (1, 2, 3):
+    for fam in (() if only else (1, 2, 3)):
         rows = parse_stk(os.path.join(REF_TEST_DIR, f"ce10-fam{fam}.stk"))
         json.dump(rows, open(os.path.join(HERE, f"ce10_fam{fam}.json"), "w"))
         print("ce10 fam", fam, len(rows))

@@ -296,12 +296,18 @@ def test_cli_outputs_byte_identical(name, tmp_path):
     synth.write_ranges(rg, case["bed"])
     cmd = [exe, "-twobit", tb, "-ranges", rg, "-outtsv", str(tmp_path / "out.tsv"), "-outfa",
            str(tmp_path / "out.fa"), "-cons", str(tmp_path / "cons.fa")] + case["flags"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert filter_stdout(r.stdout, str(tmp_path)) == case["want"]["stdout.txt"]
-    for f in ("out.tsv", "out.fa", "cons.fa"):
-        p = tmp_path / f
-        assert (p.read_text() if p.exists() else "") == case["want"][f], f
+    # default: both passes in one launch at the right call, reused at the left call if overlap
+    # avoidance changed no bound; RAMCU_PAIR=0: two launches
+    for pair in ("1", "0"):
+        for f in ("out.tsv", "out.fa", "cons.fa"):
+            if (tmp_path / f).exists():
+                (tmp_path / f).unlink()
+        r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, RAMCU_PAIR=pair))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert filter_stdout(r.stdout, str(tmp_path)) == case["want"]["stdout.txt"], pair
+        for f in ("out.tsv", "out.fa", "cons.fa"):
+            p = tmp_path / f
+            assert (p.read_text() if p.exists() else "") == case["want"][f], (f, pair)
 
 
 @pytest.fixture(scope="module")
@@ -327,11 +333,14 @@ def test_ce10_families_cli_byte_identical(ce10_standin, fam):
     outs = {f: os.path.join(d, f"fam{fam}_{f}") for f in ("out.tsv", "out.fa", "cons.fa")}
     cmd = [exe, "-twobit", twobit, "-ranges", tsvs[fam], "-outtsv", outs["out.tsv"], "-outfa", outs["out.fa"],
            "-cons", outs["cons.fa"]] + cs.STK_FLAGS
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr
-    assert filter_stdout(r.stdout, d) == want["stdout.txt"]
-    for f, p in outs.items():
-        assert (open(p).read() if os.path.exists(p) else "") == want[f], f
+    for pair in ("1", "0"):
+        r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, RAMCU_PAIR=pair))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr
+        assert filter_stdout(r.stdout, d) == want["stdout.txt"], pair
+        for f, p in outs.items():
+            assert (open(p).read() if os.path.exists(p) else "") == want[f], (f, pair)
+            if os.path.exists(p):
+                os.unlink(p)
 
 
 def _decode_packed(lib2, libn, n):
