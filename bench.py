@@ -353,7 +353,8 @@ def run_cuda(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_extend_kernel_traffic.json")))["dram_bytes_per_launch"]
+        tf = "r1_extend_kernel_traffic.json" if args.sequential else "r1_extend_kernel_pair_traffic.json"
+        traffic = json.load(open(os.path.join(ROOT, "profiles", tf)))["dram_bytes_per_launch"]
     except Exception:
         pass
 
