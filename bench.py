@@ -180,8 +180,13 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version
+    # banner there) are pointed at stderr, and the line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/null")   # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/null")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rc = RamCu(local)
     stream = torch.cuda.Stream()          # a real (non-default) stream, shared with the C-ABI
@@ -403,7 +408,7 @@ def run_cuda(args):
             "clocks": clocks}
     if fam_info:
         line["family_batch"] = fam_info
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

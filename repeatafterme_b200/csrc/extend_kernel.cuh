@@ -96,6 +96,17 @@ __device__ __forceinline__ int group_max(int v, const int gl, const int lane)
       v = max(v, __shfl_xor_sync(kFull, v, d));
     return v;
   }
+  if (G <= 7)
+  {
+    // rotate through the group: G-1 shuffles from fixed source lanes (spare lanes above the last
+    // whole group read wrapped lanes; their result is never used)
+    const int base = lane - gl;
+    int m = v;
+#pragma unroll
+    for (int d = 1; d < G; ++d)
+      m = max(m, __shfl_sync(kFull, v, (base + ((gl + d >= G) ? gl + d - G : gl + d)) & 31));
+    return m;
+  }
 #pragma unroll
   for (int d = 1; d < G; d <<= 1)
   {
@@ -448,7 +459,9 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   const int B = F->B, W = WS ? WS : F->W;
   const int go = F->go, ge = F->ge, goe = go + ge, cap = F->cap, minimp = F->minimp;
   const int L = F->L, stop = F->stop, n_ext = F->n_ext, n_ctas = F->n_ctas;
-  const bool gaps_ok = (go <= 0) && (ge <= 0);
+  // fast path: non-positive gaps (the carry peaks at a lane's first cell) of modest size (the scan
+  // adds kNegInf to travelling scores, see below)
+  const bool gaps_ok = (go <= 0) && (ge <= 0) && (go >= -100000) && ((long long) ge * (2 * F->B + 1) >= -(1 << 20));
   const unsigned char *forced = F->forced;
   int *dbg_rows = F->dbg_rows;
   const bool dbg_any = (F->dbg_rows != nullptr) || (F->dbg_best != nullptr);
@@ -548,23 +561,25 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         band_pass<C, G, WS, false, 4, false, true, false, true>(Sp, Gp, SpN, GpN, win, lutb, 0, go, ge, sin4,
                                                    gin, agg, best, 0, idx_dummy, gl, W, B, r,
                                                    tmin, tmax);
+        // lanes without a left neighbour at distance d add kNegInf instead of being predicated:
+        // every value that travels is a real cell score here (>= kNeg - |small|), so the sum stays
+        // above INT_MIN and below every real score
 #pragma unroll
         for (int d = 1; d < G; d <<= 1)
         {
+          const int pen = (gl >= d) ? d * C * ge : kNegInf;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            agg[a] = imax(agg[a], __shfl_up_sync(kFull, agg[a], d) + pen);
+        }
+        {
+          const int pen = (gl > 0) ? ge : kNegInf;
 #pragma unroll
           for (int a = 0; a < 4; ++a)
           {
-            const int up = __shfl_up_sync(kFull, agg[a], d);
-            if (gl >= d)
-              agg[a] = imax(agg[a], up + d * C * ge);
+            carry[a] = (G > 1) ? __shfl_up_sync(kFull, agg[a], 1) : 0;
+            best[a] = imax(best[a], carry[a] + pen);   // ge <= 0: the carry peaks at cell 0
           }
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-        {
-          carry[a] = (G > 1) ? __shfl_up_sync(kFull, agg[a], 1) : 0;
-          if (gl > 0)
-            best[a] = imax(best[a], carry[a] + ge);   // ge <= 0: the carry peaks at cell 0
         }
       }
       else

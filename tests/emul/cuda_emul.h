@@ -87,6 +87,16 @@ static inline int __reduce_add_sync(unsigned, int v)
   pthread_barrier_wait(&emul_warp->bar);
   return (int) s;
 }
+static inline int __reduce_max_sync(unsigned, int v)
+{
+  const int lane = threadIdx.x & 31;
+  emul_warp->buf[lane] = v;
+  pthread_barrier_wait(&emul_warp->bar);
+  int m = (int) emul_warp->buf[0];
+  for (int i = 1; i < 32; ++i) m = ((int) emul_warp->buf[i] > m) ? (int) emul_warp->buf[i] : m;
+  pthread_barrier_wait(&emul_warp->bar);
+  return m;
+}
 static inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __sync_fetch_and_or(p, v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __sync_fetch_and_add(p, v); }
