@@ -787,20 +787,25 @@ extern "C" int ramcu_job_fetch(ramcu_ctx *c, ramcu_job *j, uint8_t *master_out, 
   }
   if (j->d_dbg_wait)
   {
-    std::vector<long long> w((size_t) 2 * j->solo.n_ctas);
+    const int n_stat = std::max(j->solo.n_ctas, j->batch_ctas);
+    std::vector<long long> w((size_t) 2 * n_stat);
     CK(cudaMemcpy(w.data(), j->d_dbg_wait, w.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     CK(cudaMemset(j->d_dbg_wait, 0, w.size() * sizeof(long long)));
     long long wmin = 1LL << 62, wmax = 0, wsum = 0, tmax = 0;
-    for (int i = 0; i < j->solo.n_ctas; ++i)
+    int n_seen = 0;
+    for (int i = 0; i < n_stat; ++i)
     {
+      if (w[2 * i + 1] == 0)
+        continue;   // CTA index not used by the layout that ran
+      ++n_seen;
       wmin = std::min(wmin, w[2 * i]);
       wmax = std::max(wmax, w[2 * i]);
       wsum += w[2 * i];
       tmax = std::max(tmax, w[2 * i + 1]);
     }
     fprintf(stderr, "[ramcu stats] ctas=%d rows=%d cycles/row: total %.0f, exchange wait min %.0f avg %.0f max %.0f\n",
-            j->solo.n_ctas, r4[1], (double) tmax / std::max(r4[1], 1), (double) wmin / std::max(r4[1], 1),
-            (double) wsum / j->solo.n_ctas / std::max(r4[1], 1), (double) wmax / std::max(r4[1], 1));
+            n_seen, r4[1], (double) tmax / std::max(r4[1], 1), (double) wmin / std::max(r4[1], 1),
+            (double) wsum / std::max(n_seen, 1) / std::max(r4[1], 1), (double) wmax / std::max(r4[1], 1));
   }
   if (master_out && r4[1] > 0)
     CK(cudaMemcpy(master_out, j->d_master, r4[1], cudaMemcpyDeviceToHost));
@@ -980,6 +985,7 @@ extern "C" int ramcu_job_create_pair(ramcu_ctx *c, ramcu_library *lib, int n_cor
   }
   if (!together)   // ramcu_batch_run then launches each pass on its own, one after the other
     (*right)->batch_ctas = (*left)->batch_ctas = 0;
+
   return RAMCU_OK;
 }
 
