@@ -193,6 +193,22 @@ int ramcu_extend_pair(ramcu_ctx *ctx, ramcu_library *lib, int n_cores, const ram
                       ramcu_result_t *res_right, uint8_t *master_left, int32_t *ext_len_left,
                       int32_t *score_add_left, ramcu_result_t *res_left);
 
+/* -outmat (ram_extend.c:1115-1132, bnw_extend.c:1027-1044): ramcu_extend() that also returns, for
+ * every processed row r < res->rows_processed and every core i extendable in `direction`,
+ *   path_state_out[(r * n_cores + i) * W + k]   state of the best path into band cell k (offset k - B) of
+ *                                                the committed row: 0 substitution, 1 deletion, 2 insertion
+ *                                                (the reference prints the base / '-' / the lowercase base)
+ *   row_best_out[r * n_cores + i]               compute_nw_row()'s return value for the chosen base
+ *   row_best_idx_out[r * n_cores + i]           band index of its first best cell
+ *                                                (curr_row_best_col_idx - row_idx + BANDWIDTH)
+ * with W = 2 * bandwidth + 1; arrays hold params->L rows; entries of other cores are left untouched.
+ * Debug path: L x n_cores x W is limited to 4 Gi cells. */
+int ramcu_extend_paths(ramcu_ctx *ctx, ramcu_library *lib, int direction, int n_cores,
+                       const ramcu_core_t *cores, const ramcu_scoring_t *scoring,
+                       const ramcu_params_t *params, uint8_t *master_out, int32_t *ext_len_out,
+                       int32_t *score_add_out, ramcu_result_t *res, uint8_t *path_state_out,
+                       int32_t *row_best_out, int32_t *row_best_idx_out);
+
 /* Test-only second boundary (compute_nw_row, bnw_extend.h:52-58). Runs the extension kernel for
  * `n_rows` rows with the consensus FORCED to forced_cons[r] (NULL = argmax as usual) and returns
  *   rows_out : [n_rows][n_cores][2*B+1][2] committed band rows ([..][0]=sub, [..][1]=gap);

@@ -36,7 +36,7 @@ ABI_SYMBOLS = (
     "ramcu_device_info", "ramcu_int32_peak", "ramcu_scoring_by_name", "ramcu_library_upload",
     "ramcu_library_from_device", "ramcu_library_from_twobit", "ramcu_library_download", "ramcu_library_free", "ramcu_extend", "ramcu_job_create",
     "ramcu_job_run", "ramcu_job_fetch", "ramcu_job_free", "ramcu_batch_run", "ramcu_debug_rows",
-    "ramcu_job_create_pair", "ramcu_extend_pair",
+    "ramcu_job_create_pair", "ramcu_extend_pair", "ramcu_extend_paths",
 )
 
 
@@ -140,6 +140,8 @@ def load_ramcu(path: str = LIB_PATH) -> C.CDLL:
     lib.ramcu_job_create_pair.argtypes = [vp, vp, i32, vp, P(Scoring), P(Params), P(vp), P(vp)]
     lib.ramcu_extend_pair.argtypes = [vp, vp, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult),
                                       vp, vp, vp, P(ExtendResult)]
+    lib.ramcu_extend_paths.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult),
+                                       vp, vp, vp]
     lib.ramcu_debug_rows.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), i32, vp, vp, vp, vp]
     for name in ABI_SYMBOLS:
         if name not in ("ramcu_last_error", "ramcu_destroy"):
@@ -245,6 +247,25 @@ class RamCu:
                                           C.byref(scoring), C.byref(params), master.ctypes.data,
                                           ext_len.ctypes.data, score_add.ctypes.data, C.byref(res)))
         return res, master[: res.rows_processed].copy(), ext_len, score_add
+
+    def extend_paths(self, lib_h, direction: int, cores: np.ndarray, scoring: Scoring, params: Params):
+        """ramcu_extend_paths: extend() plus the -outmat data (path state per band cell, best score and
+        first best band index per row and core)."""
+        cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+        n, W, L = cores.size, 2 * params.bandwidth + 1, max(params.L, 1)
+        master = np.zeros(L, dtype=np.uint8)
+        ext_len = np.zeros(n, dtype=np.int32)
+        score_add = np.zeros(n, dtype=np.int32)
+        state = np.zeros((L, n, W), dtype=np.uint8)
+        best = np.zeros((L, n), dtype=np.int32)
+        idx = np.zeros((L, n), dtype=np.int32)
+        res = ExtendResult()
+        self._check(self.lib.ramcu_extend_paths(self.ctx, lib_h, direction, n, cores.ctypes.data, C.byref(scoring),
+                                                C.byref(params), master.ctypes.data, ext_len.ctypes.data,
+                                                score_add.ctypes.data, C.byref(res), state.ctypes.data,
+                                                best.ctypes.data, idx.ctypes.data))
+        rp = res.rows_processed
+        return res, master[:rp].copy(), ext_len, score_add, state[:rp], best[:rp], idx[:rp]
 
     # -- split form -------------------------------------------------------------------------
     def job_create(self, lib_h, direction: int, cores: np.ndarray, scoring: Scoring, params: Params):

@@ -66,6 +66,10 @@ struct FamDev
   int *dbg_rows;          // debug: [rows][n_ext][W][2]
   int *dbg_best;          // debug: [rows][n_ext][4]
   int *dbg_sums;          // debug: [rows][4]
+  unsigned char *dbg_path;   // -outmat: [rows][n_ext][W] state of the best path into each cell of the
+                             // committed row: 0 substitution, 1 deletion, 2 insertion (bnw_extend.c:1027-1044)
+  int *dbg_del;           // -outmat scratch: [n_ext][W] deletion term of the row being committed
+  int *dbg_idx;           // -outmat: [rows][n_ext] band index of the row's first best cell
   long long *dbg_wait;    // diagnostics: per CTA [0] cycles spent in the grid exchange [1] total cycles
   int n_ext, n_ctas, cta0, B;
   int W, go, ge, cap;
@@ -465,6 +469,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   const unsigned char *forced = F->forced;
   int *dbg_rows = F->dbg_rows;
   const bool dbg_any = (F->dbg_rows != nullptr) || (F->dbg_best != nullptr);
+  unsigned char *dbg_path = F->dbg_path;
 
   // balanced partition of the family's instances over its CTAs (n_ctas <= n_ext)
   const int first = (int) ((long long) cta_in_fam * n_ext / n_ctas);
@@ -511,7 +516,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     const int tfirst = r - B + gl * C;
     const bool lane_ok = (tfirst >= tmin) && (tfirst + nreal - 1 <= tmax);
     const bool dead = (r - B > tmax) && (r >= B);   // every cell out of bounds, for good
-    const bool alldead = (dbg_rows == nullptr) && __all_sync(kFull, dead);
+    const bool alldead = (dbg_rows == nullptr) && (dbg_path == nullptr) && __all_sync(kFull, dead);
     const bool fast = (WS != 0) && gaps_ok && __all_sync(kFull, lane_ok);
 
     int best[4] = {kOob, kOob, kOob, kOob};
@@ -708,6 +713,14 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       int cg[1] = {(gl == 0) ? (kNeg - ge) : sel4(besta, carry[0], carry[1], carry[2], carry[3])};
       int gout1[1], nob[1] = {0};
       int idx = kBig;
+      if (dbg_path != nullptr && valid)
+      {
+        // Gp holds the deletion term D of every cell until the commit overwrites it
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+          if (gl * C + k < W)
+            F->dbg_del[(size_t) inst * W + gl * C + k] = Gp[k];
+      }
       if (fast)
         band_pass<C, G, WS, false, 1, true, false, true, false>(Sp, Gp, SpN, GpN, win, lutb, besta, go, ge, cs,
                                                    cg, gout1, nob, bestb, idx, gl, W, B, r, tmin,
@@ -736,6 +749,25 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
             o[1] = Gp[k];
           }
         }
+      }
+      if (dbg_path != nullptr && valid)
+      {
+        // sub == cell -> substitution, else del == cell -> deletion, else insertion
+        // (bnw_extend.c:1036-1041; each thread reads back the D it stored above)
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+        {
+          const int K = gl * C + k;
+          if (K < W)
+          {
+            const int cell = imax(Sp[k], Gp[k]);
+            const int del = F->dbg_del[(size_t) inst * W + K];
+            dbg_path[((size_t) r * n_ext + inst) * W + K] =
+              (unsigned char) ((Sp[k] == cell) ? 0 : (del == cell) ? 1 : 2);
+          }
+        }
+        if (gl == 0)
+          F->dbg_idx[(size_t) r * n_ext + inst] = kidx;
       }
     }
 

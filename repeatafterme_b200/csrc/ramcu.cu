@@ -115,6 +115,8 @@ struct ramcu_job
   int *d_cta_fam;     // zeros, n_ctas
   unsigned char *d_forced;
   int *d_dbg_rows, *d_dbg_best, *d_dbg_sums;
+  unsigned char *d_dbg_path;   // -outmat mode (negative dbg_rows in job_create_impl)
+  int *d_dbg_del, *d_dbg_idx;
   long long *d_dbg_wait;   // RAMCU_STATS=1 diagnostics
   bool ran, timed;
 };
@@ -582,7 +584,8 @@ static size_t slots_bytes(int n_ctas, int L)
 static void free_job_device(ramcu_ctx *c, ramcu_job *j)
 {
   void *ptrs[] = {j->d_inst, j->d_master, j->d_thigh, j->d_tpos, j->d_result, j->d_slots, j->d_fam,
-                  j->d_cta_fam, j->d_forced, j->d_dbg_rows, j->d_dbg_best, j->d_dbg_sums, j->d_dbg_wait};
+                  j->d_cta_fam, j->d_forced, j->d_dbg_rows, j->d_dbg_best, j->d_dbg_sums, j->d_dbg_wait,
+                  j->d_dbg_path, j->d_dbg_del, j->d_dbg_idx};
   for (void *p : ptrs)
     if (p)
     {
@@ -660,6 +663,17 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     CK(cudaMallocAsync(&j->d_fam, sizeof(FamDev), c->stream));
     CK(cudaMallocAsync(&j->d_cta_fam, max_ctas * sizeof(int), c->stream));
     CK(cudaMemsetAsync(j->d_cta_fam, 0, max_ctas * sizeof(int), c->stream));
+    if (dbg_rows < 0)   // -outmat mode: path states of -dbg_rows rows, no forced consensus
+    {
+      const size_t rows = (size_t) -dbg_rows;
+      CK(cudaMallocAsync(&j->d_dbg_path, rows * j->n_ext * W, c->stream));
+      CK(cudaMemsetAsync(j->d_dbg_path, 0, rows * j->n_ext * W, c->stream));
+      CK(cudaMallocAsync(&j->d_dbg_del, (size_t) j->n_ext * W * sizeof(int), c->stream));
+      CK(cudaMallocAsync(&j->d_dbg_idx, rows * j->n_ext * sizeof(int), c->stream));
+      CK(cudaMemsetAsync(j->d_dbg_idx, 0, rows * j->n_ext * sizeof(int), c->stream));
+      CK(cudaMallocAsync(&j->d_dbg_best, rows * j->n_ext * 4 * sizeof(int), c->stream));
+      CK(cudaMallocAsync(&j->d_dbg_sums, rows * 4 * sizeof(int), c->stream));
+    }
     if (dbg_rows > 0)
     {
       CK(cudaMallocAsync(&j->d_dbg_rows, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int), c->stream));
@@ -690,6 +704,9 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     f.slots = j->d_slots;
     f.forced = j->d_forced;
     f.dbg_rows = j->d_dbg_rows;
+    f.dbg_path = j->d_dbg_path;
+    f.dbg_del = j->d_dbg_del;
+    f.dbg_idx = j->d_dbg_idx;
     f.dbg_best = j->d_dbg_best;
     f.dbg_sums = j->d_dbg_sums;
     CK(cudaMemcpyAsync(j->d_fam, &f, sizeof(f), cudaMemcpyHostToDevice, c->stream));
@@ -1006,6 +1023,59 @@ extern "C" int ramcu_extend_pair(ramcu_ctx *c, ramcu_library *lib, int n_cores, 
     rc = ramcu_job_fetch(c, jobs[1], master_left, ext_len_left, score_add_left, res_left);
   ramcu_job_free(c, jobs[0]);
   ramcu_job_free(c, jobs[1]);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// -outmat: one extend_alignment() call that also reports, for every processed row and every
+// extendable core, the state of the best path into each band cell, the row's best score and the
+// band index of its first best cell (what compute_nw_row() writes into pathString and returns in
+// the reference's 5th pass, bnw_extend.c:1020-1044, ram_extend.c:1115-1132)
+// ------------------------------------------------------------------------------------------
+extern "C" int ramcu_extend_paths(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
+                                  const ramcu_core_t *cores, const ramcu_scoring_t *sc,
+                                  const ramcu_params_t *pr, uint8_t *master_out, int32_t *ext_len_out,
+                                  int32_t *score_add_out, ramcu_result_t *res, uint8_t *path_state_out,
+                                  int32_t *row_best_out, int32_t *row_best_idx_out)
+{
+  if (!pr || !path_state_out || !row_best_out || !row_best_idx_out)
+    return fail(RAMCU_ERR_ARG, "ramcu_extend_paths: NULL argument");
+  if (pr->L <= 0 || n_cores <= 0)
+    return ramcu_extend(c, lib, direction, n_cores, cores, sc, pr, master_out, ext_len_out, score_add_out, res);
+  const size_t W = 2 * (size_t) pr->bandwidth + 1;
+  if ((size_t) pr->L * (size_t) n_cores * W > ((size_t) 4 << 30))
+    return fail(RAMCU_ERR_UNSUPPORTED, "ramcu_extend_paths: L x cores x band = %zu cells of path state (limit 4 Gi)",
+                (size_t) pr->L * (size_t) n_cores * W);
+  ramcu_job *j = nullptr;
+  int rc = job_create_impl(c, lib, direction, n_cores, cores, sc, pr, -pr->L, nullptr, &j);
+  if (rc)
+    return rc;
+  if (j->n_ctas > 0)
+    rc = ramcu_job_run(c, j);
+  ramcu_result_t r0;
+  if (!rc)
+    rc = ramcu_job_fetch(c, j, master_out, ext_len_out, score_add_out, &r0);
+  if (!rc && res)
+    *res = r0;
+  if (!rc && j->n_ctas > 0 && r0.rows_processed > 0)
+  {
+    const size_t rows = (size_t) r0.rows_processed, ne = (size_t) j->n_ext;
+    std::vector<unsigned char> path(rows * ne * W), cons(rows);
+    std::vector<int> best(rows * ne * 4), idx(rows * ne);
+    CK(cudaMemcpy(path.data(), j->d_dbg_path, path.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(best.data(), j->d_dbg_best, best.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(idx.data(), j->d_dbg_idx, idx.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cons.data(), j->d_master, rows, cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < rows; ++r)
+      for (size_t e = 0; e < ne; ++e)
+      {
+        const size_t i = (size_t) j->orig[e];
+        memcpy(path_state_out + (r * (size_t) n_cores + i) * W, path.data() + (r * ne + e) * W, W);
+        row_best_out[r * (size_t) n_cores + i] = best[(r * ne + e) * 4 + (cons[r] & 3)];
+        row_best_idx_out[r * (size_t) n_cores + i] = idx[r * ne + e];
+      }
+  }
+  ramcu_job_free(c, j);
   return rc;
 }
 

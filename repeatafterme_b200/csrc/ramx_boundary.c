@@ -29,6 +29,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
+#include <ctype.h>
 
 #include "common.h"        /* struct coreAlignment        (reference, -I$(REF)) */
 #include "sequence.h"      /* struct sequenceLibrary, SYM_N */
@@ -100,11 +101,10 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
     else
       printf("extend_alignment(left): Called with %d edges\n", N);
   }
-  if (VERBOSE >= 10 || pathStringFile != NULL)
+  if (VERBOSE >= 10)
   {
-    /* per-row dumps of every DP row (-vvvv.., -outmat) are debug paths of the CPU loop */
-    printf("RAMExtend (CUDA build): -vvvv/-vvvvv/-vvvvvv and -outmat are not available on the "
-           "GPU path\n");
+    /* per-row dumps of every DP row (-vvvv..) are debug paths of the CPU loop */
+    printf("RAMExtend (CUDA build): -vvvv/-vvvvv/-vvvvvv are not available on the GPU path\n");
     exit(1);
   }
 
@@ -170,6 +170,61 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
   pr.L = L;
   pr.when_to_stop = WHEN_TO_STOP;
 
+  if (pathStringFile != NULL)
+  {
+    /* -outmat: the kernel also reports the path state of every band cell of every committed row;
+     * the lines of ram_extend.c:1122-1132 are written here, in the reference's order */
+    const size_t W = 2 * (size_t) BANDWIDTH + 1;
+    const size_t cells = (size_t) (L > 0 ? L : 1) * (size_t) (n > 0 ? n : 1);
+    uint8_t *state = (uint8_t *) calloc(cells * W, 1);
+    int32_t *rbest = (int32_t *) calloc(cells, sizeof(int32_t));
+    int32_t *ridx = (int32_t *) calloc(cells, sizeof(int32_t));
+    char *path = (char *) malloc(W + 1);
+    if (!state || !rbest || !ridx || !path)
+    {
+      printf("extend_alignment: Error could not allocate memory for the path strings\n");
+      exit(1);
+    }
+    ahead_drop();
+    if (ramcu_extend_paths(g_ctx, g_lib, direction ? 1 : 0, n, cores, &sc, &pr, cons, ext_len, score_add,
+                           &res, state, rbest, ridx) != RAMCU_OK)
+      die("ramcu_extend_paths");
+    for (r = 0; r < res.rows_processed; r++)
+    {
+      int i = 0;
+      for (c = coreAlign; c != NULL && i < n; c = c->next, i++)
+      {
+        uint64_t start_seq_pos;
+        int offset;
+        if (!((direction && c->rightExtendable) || (!direction && c->leftExtendable)))
+          continue;
+        /* bnw_extend.c:778-788, 824-837 */
+        if (direction)
+          start_seq_pos = c->orient ? c->rightSeqPos - 1 : c->rightSeqPos + 1;
+        else
+          start_seq_pos = c->orient ? c->leftSeqPos + 1 : c->leftSeqPos - 1;
+        for (offset = -BANDWIDTH; offset < BANDWIDTH; offset++)   /* the last cell is cut off (:1124) */
+        {
+          const int seq_offset = ((direction ? 1 : 0) == (c->orient ? 1 : 0)) ? -offset - r : offset + r;
+          const uint64_t seq_idx = start_seq_pos + seq_offset;
+          const uint8_t st = state[((size_t) r * n + i) * W + (size_t) (offset + BANDWIDTH)];
+          char base = 'X';
+          if (seq_idx >= c->lowerSeqBound && seq_idx <= c->upperSeqBound)
+            base = num_to_char(seqLib->sequence[seq_idx]);
+          path[offset + BANDWIDTH] = (base == 'X' || st == 0) ? base : (st == 1) ? '-' : (char) tolower(base);
+        }
+        path[2 * BANDWIDTH] = '\0';
+        fprintf(pathStringFile, direction ? "dir=right" : "dir=left");
+        fprintf(pathStringFile, ":n=%d:row=%d: %s best:score=%d:offset=%d:cons=%c\n", i, r, path,
+                rbest[(size_t) r * n + i], ridx[(size_t) r * n + i], num_to_char((char) cons[r]));
+      }
+    }
+    free(state);
+    free(rbest);
+    free(ridx);
+    free(path);
+  }
+  else
   {
     const char *pe = getenv("RAMCU_PAIR");
     const int pair_ok = !(pe && atoi(pe) == 0);

@@ -113,6 +113,16 @@ def main():
             for f in ("out.tsv", "out.fa", "cons.fa"):
                 src = os.path.join(tmp, f)
                 open(os.path.join(d, f), "w").write(open(src).read() if os.path.exists(src) else "")
+            # -outmat (ram_extend.c:1122-1132): the file is large, so its sha256, its line count and its
+            # first and last 40 lines are the golden
+            import hashlib
+            mat = os.path.join(tmp, "mat.txt")
+            r2 = subprocess.run(cmd + ["-outmat", mat], capture_output=True, text=True)
+            assert r2.returncode == 0, r2.stdout + r2.stderr
+            data = open(mat).read()
+            lines = data.splitlines()
+            json.dump(dict(sha256=hashlib.sha256(data.encode()).hexdigest(), lines=len(lines), head=lines[:40],
+                           tail=lines[-40:]), open(os.path.join(d, "outmat.json"), "w"), indent=0)
         m = re.findall(r"Extended (?:right|left ): (\d+) bp", r.stdout)
         print("cli", name, m)
 

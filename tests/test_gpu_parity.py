@@ -310,6 +310,37 @@ def test_cli_outputs_byte_identical(name, tmp_path):
             assert (p.read_text() if p.exists() else "") == case["want"][f], (f, pair)
 
 
+@pytest.mark.parametrize("name", gio.cli_case_names())
+def test_cli_outmat_byte_identical(name, tmp_path):
+    """-outmat (per-row path strings of every extendable core, ram_extend.c:1122-1132 /
+    bnw_extend.c:1027-1044), written from the kernel's path states, against the reference binary's
+    file (sha256, line count, first and last lines)."""
+    import hashlib
+    import json
+    exe = os.path.join(ROOT, "repeatafterme_b200", "bin", "RAMExtend")
+    if not os.path.exists(exe):
+        pytest.skip("bin/RAMExtend not built (needs the reference's host objects)")
+    gpath = os.path.join(ROOT, "tests", "golden", f"cli_{name}", "outmat.json")
+    if not os.path.exists(gpath):
+        pytest.skip("no -outmat golden for this case")
+    want = json.load(open(gpath))
+    case = gio.load_cli(name)
+    tb, rg, mat = str(tmp_path / "in.2bit"), str(tmp_path / "in.tsv"), str(tmp_path / "mat.txt")
+    synth.write_twobit(tb, case["names"], case["seqs"])
+    synth.write_ranges(rg, case["bed"])
+    cmd = [exe, "-twobit", tb, "-ranges", rg, "-outmat", mat, "-cons", str(tmp_path / "cons.fa")] + case["flags"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    data = open(mat).read()
+    lines = data.splitlines()
+    assert len(lines) == want["lines"]
+    for i, (a, b) in enumerate(zip(lines[:40], want["head"])):
+        assert a == b, f"line {i}"
+    assert lines[-40:] == want["tail"]
+    assert hashlib.sha256(data.encode()).hexdigest() == want["sha256"]
+    assert (tmp_path / "cons.fa").read_text() == case["want"]["cons.fa"]
+
+
 @pytest.fixture(scope="module")
 def ce10_standin(tmp_path_factory):
     from tests import ce10_standin as cs
