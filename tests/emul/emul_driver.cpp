@@ -102,12 +102,13 @@ extern "C" void emul_cfg(int i, int *C, int *G, int *WS) { *C = kCfgs[i].C; *G =
 
 // Same contract as ramcu_extend() / ramcu_debug_rows() (include/ramcu.h), plus an explicit band
 // tiling (C, G, WS) and CTA size. dbg_* and forced may be NULL.
-extern "C" int emul_extend(int C, int G, int WS, int threads, const uint8_t *seq, uint64_t seq_len,
-                           int direction, int n_cores, const ramcu_core_t *cores,
-                           const ramcu_scoring_t *sc, const ramcu_params_t *pr,
-                           uint8_t *master_out, int32_t *ext_len_out, int32_t *score_add_out,
-                           ramcu_result_t *res, int dbg_nrows, const uint8_t *forced,
-                           int32_t *rows_out, int32_t *best_out, int32_t *sums_out)
+static int emul_extend_impl(int C, int G, int WS, int threads, const uint8_t *seq, uint64_t seq_len,
+                            int direction, int n_cores, const ramcu_core_t *cores,
+                            const ramcu_scoring_t *sc, const ramcu_params_t *pr,
+                            uint8_t *master_out, int32_t *ext_len_out, int32_t *score_add_out,
+                            ramcu_result_t *res, int dbg_nrows, const uint8_t *forced,
+                            int32_t *rows_out, int32_t *best_out, int32_t *sums_out,
+                            uint8_t *path_out, int32_t *pbest_out, int32_t *pidx_out)
 {
   const Cfg *cfg = nullptr;
   for (const Cfg &c : kCfgs)
@@ -175,6 +176,21 @@ extern "C" int emul_extend(int C, int G, int WS, int threads, const uint8_t *seq
     f.dbg_sums = dsums.data();
     f.forced = forced;
   }
+  std::vector<unsigned char> dpath;
+  std::vector<int> ddel, didx;
+  if (path_out)   // -outmat mode (ramcu_extend_paths)
+  {
+    dpath.assign((size_t) p2.L * n_ext * W, 0);
+    ddel.assign((size_t) n_ext * W, 0);
+    didx.assign((size_t) p2.L * n_ext, 0);
+    dbest.assign((size_t) p2.L * n_ext * 4, 0);
+    dsums.assign((size_t) p2.L * 4, 0);
+    f.dbg_path = dpath.data();
+    f.dbg_del = ddel.data();
+    f.dbg_idx = didx.data();
+    f.dbg_best = dbest.data();
+    f.dbg_sums = dsums.data();
+  }
   int ticket = 0;
   LaunchArgs a = {};
   a.fn = cfg->fn;
@@ -193,6 +209,14 @@ extern "C" int emul_extend(int C, int G, int WS, int threads, const uint8_t *seq
   if (master_out)
     memcpy(master_out, master.data(), result[1]);
   map_results(n_cores, orig, thigh.data(), tpos.data(), ext_len_out, score_add_out);
+  if (path_out)
+    for (int r = 0; r < result[1]; ++r)
+      for (int e = 0; e < n_ext; ++e)
+      {
+        memcpy(path_out + ((size_t) r * n_cores + orig[e]) * W, dpath.data() + ((size_t) r * n_ext + e) * W, W);
+        pbest_out[(size_t) r * n_cores + orig[e]] = dbest[((size_t) r * n_ext + e) * 4 + (master[r] & 3)];
+        pidx_out[(size_t) r * n_cores + orig[e]] = didx[(size_t) r * n_ext + e];
+      }
   for (int r = 0; r < dbg_nrows; ++r)
   {
     for (int e = 0; e < n_ext; ++e)
@@ -208,4 +232,28 @@ extern "C" int emul_extend(int C, int G, int WS, int threads, const uint8_t *seq
       memcpy(sums_out + (size_t) r * 4, dsums.data() + (size_t) r * 4, 4 * sizeof(int));
   }
   return 0;
+}
+
+extern "C" int emul_extend(int C, int G, int WS, int threads, const uint8_t *seq, uint64_t seq_len,
+                           int direction, int n_cores, const ramcu_core_t *cores,
+                           const ramcu_scoring_t *sc, const ramcu_params_t *pr,
+                           uint8_t *master_out, int32_t *ext_len_out, int32_t *score_add_out,
+                           ramcu_result_t *res, int dbg_nrows, const uint8_t *forced,
+                           int32_t *rows_out, int32_t *best_out, int32_t *sums_out)
+{
+  return emul_extend_impl(C, G, WS, threads, seq, seq_len, direction, n_cores, cores, sc, pr, master_out,
+                          ext_len_out, score_add_out, res, dbg_nrows, forced, rows_out, best_out, sums_out,
+                          nullptr, nullptr, nullptr);
+}
+
+// Same contract as ramcu_extend_paths() (include/ramcu.h)
+extern "C" int emul_extend_paths(int C, int G, int WS, int threads, const uint8_t *seq, uint64_t seq_len,
+                                 int direction, int n_cores, const ramcu_core_t *cores,
+                                 const ramcu_scoring_t *sc, const ramcu_params_t *pr,
+                                 uint8_t *master_out, int32_t *ext_len_out, int32_t *score_add_out,
+                                 ramcu_result_t *res, uint8_t *path_out, int32_t *pbest_out, int32_t *pidx_out)
+{
+  return emul_extend_impl(C, G, WS, threads, seq, seq_len, direction, n_cores, cores, sc, pr, master_out,
+                          ext_len_out, score_add_out, res, 0, nullptr, nullptr, nullptr, nullptr, path_out,
+                          pbest_out, pidx_out);
 }

@@ -189,6 +189,8 @@ class Emulator:
         lib.emul_extend.argtypes = [i32, i32, i32, i32, vp, u64, i32, i32, vp, P(Scoring), P(Params),
                                     vp, vp, vp, P(ExtendResult), i32, vp, vp, vp, vp]
         lib.emul_cfg.argtypes = [i32, P(i32), P(i32), P(i32)]
+        lib.emul_extend_paths.argtypes = [i32, i32, i32, i32, vp, u64, i32, i32, vp, P(Scoring), P(Params),
+                                          vp, vp, vp, P(ExtendResult), vp, vp, vp]
 
     def configs(self):
         out = []
@@ -230,6 +232,57 @@ class Emulator:
                     stop_row=res.stop_row, hit_limit=res.hit_limit, max_score=res.max_score,
                     n_extendable=res.n_extendable, master=master[: res.rows_processed].copy(),
                     ext_len=ext_len, score_add=score_add, rows=rows, best=best, sums=sums)
+
+
+def emul_extend_paths(emul, cfg, direction, cores, seq, sc, p, threads=128):
+    """ramcu_extend_paths through the CPU emulation of the kernel source"""
+    cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    n, W, L = cores.size, 2 * p.bandwidth + 1, max(p.L, 1)
+    master = np.zeros(L + 1, dtype=np.uint8)
+    ext_len = np.zeros(n, dtype=np.int32)
+    score_add = np.zeros(n, dtype=np.int32)
+    state = np.zeros((L, n, W), dtype=np.uint8)
+    best = np.zeros((L, n), dtype=np.int32)
+    idx = np.zeros((L, n), dtype=np.int32)
+    res = ExtendResult()
+    rc = emul.lib.emul_extend_paths(cfg[0], cfg[1], cfg[2], threads, seq.ctypes.data, seq.size, direction, n,
+                                    cores.ctypes.data, C.byref(sc), C.byref(p), master.ctypes.data,
+                                    ext_len.ctypes.data, score_add.ctypes.data, C.byref(res),
+                                    state.ctypes.data, best.ctypes.data, idx.ctypes.data)
+    assert rc == 0, f"emul_extend_paths rc={rc}"
+    rp = res.rows_processed
+    return dict(rows_processed=rp, extended_bp=res.extended_bp, master=master[:rp].copy(), state=state[:rp],
+                best=best[:rp], idx=idx[:rp])
+
+
+def format_outmat(direction, cores, seq, bandwidth, master, state, best, idx):
+    """The -outmat lines of ram_extend.c:1122-1132 from path states (0 substitution, 1 deletion,
+    2 insertion): test-side restatement of what csrc/ramx_boundary.c prints."""
+    out = []
+    B = bandwidth
+    for r in range(len(master)):
+        for i, c in enumerate(cores):
+            if not (c["right_extendable"] if direction else c["left_extendable"]):
+                continue
+            if direction:
+                start = int(c["right_seq_pos"]) + (-1 if c["orient"] else 1)
+            else:
+                start = int(c["left_seq_pos"]) + (1 if c["orient"] else -1)
+            chars = []
+            for off in range(-B, B):
+                so = (-off - r) if (bool(direction) == bool(c["orient"])) else (off + r)
+                p = start + so
+                if p < int(c["lower_seq_bound"]) or p > int(c["upper_seq_bound"]) or p < 0:
+                    chars.append("X")
+                    continue
+                v = int(seq[p])
+                base = "ACGTacgt"[v] if v < 8 else "N"
+                st = int(state[r, i, off + B])
+                chars.append(base if st == 0 else "-" if st == 1 else base.lower())
+            out.append("dir=%s:n=%d:row=%d: %s best:score=%d:offset=%d:cons=%s" % (
+                "right" if direction else "left", i, r, "".join(chars), best[r, i], idx[r, i], "ACGT"[master[r] & 3]))
+    return out
 
 
 def compare_extend(a: dict, b: dict, what=""):

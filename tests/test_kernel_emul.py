@@ -80,3 +80,28 @@ def test_emul_golden(emul, oracle, name, cfg):
     for d in (1, 0):
         got = emul.extend(cfg, d, case["cores"], case["sequence"], sc, p, threads=64)
         gio.check_against_golden(case, d, got, f"{name} dir={d}")
+
+
+@pytest.mark.parametrize("cfg", [(8, 4, 29), (29, 1, 29), (10, 3, 29)])
+def test_emul_outmat_config1(emul, oracle, cfg):
+    """-outmat path strings (ram_extend.c:1122-1132, bnw_extend.c:1027-1044) from the kernel's path
+    states for BASELINE config 1 == the file the reference binary writes (sha256 + head + tail)"""
+    import hashlib
+    import json
+    import os
+    if cfg not in emul.configs():
+        pytest.skip("tiling not in the emulator build")
+    case = gio.load_flat("config1_default")
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cli_config1_default", "outmat.json")))
+    sc = gio.oracle_scoring_for(case, oracle).to_product()
+    p = gio.params_for(case)
+    lines = []
+    for d in (1, 0):
+        got = support.emul_extend_paths(emul, cfg, d, case["cores"], case["sequence"], sc, p)
+        lines += support.format_outmat(d, case["cores"], case["sequence"], p.bandwidth, got["master"],
+                                       got["state"], got["best"], got["idx"])
+    assert len(lines) == want["lines"]
+    for i, (a, b) in enumerate(zip(lines[:40], want["head"])):
+        assert a == b, f"line {i}"
+    assert lines[-40:] == want["tail"]
+    assert hashlib.sha256(("\n".join(lines) + "\n").encode()).hexdigest() == want["sha256"]
