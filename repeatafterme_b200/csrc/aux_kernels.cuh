@@ -65,10 +65,7 @@ pack_library_kernel(const uint8_t *__restrict__ bytes, const unsigned long long 
 // 2bit-native flank feed: build the packed library straight from the .2bit file's own packed DNA
 // (kentsrc/twoBitNew.c:571-582: 4 bases per byte, first base in the top two bits, T0 C1 A2 G3),
 // without the 1-byte-per-base expansion of loadSequenceSubsetMinimal (sequence.c:752-822).
-// One thread produces 32 library bases: it finds its window (binary search over dst offsets), reads
-// the <= 12 source bytes that cover them as three 32-bit words, re-orders the bases to the little
-// endian A0 C1 G2 T3 code of lib2 and stores one 64-bit word. N-blocks are applied by
-// nmask_ranges_kernel afterwards.
+// N-blocks are applied by nmask_ranges_kernel afterwards.
 struct WindowDev
 {
   unsigned long long dst;      // first library position of the window
@@ -77,14 +74,14 @@ struct WindowDev
   unsigned long long src_base; // index of the window's first base inside the record
 };
 
-__global__ void __launch_bounds__(256)
-twobit_windows_kernel(const uint8_t *__restrict__ blob, const unsigned long long blob_bytes,
-                      const WindowDev *__restrict__ win, const int n_win,
-                      const unsigned long long total, uint32_t *__restrict__ lib2,
-                      const unsigned long long n_chunks)
+// one 32-base chunk, base by base: chunks that straddle windows, the library's tail and sources
+// too close to the end of the blob for whole 16-byte loads
+__device__ __forceinline__ void twobit_chunk_slow(const uint8_t *__restrict__ blob,
+                                                  const unsigned long long blob_bytes,
+                                                  const WindowDev *__restrict__ win, const int n_win,
+                                                  const unsigned long long total,
+                                                  uint32_t *__restrict__ lib2, const unsigned long long ch)
 {
-  for (unsigned long long ch = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
-       ch < n_chunks; ch += (unsigned long long) gridDim.x * blockDim.x)
   {
     const unsigned long long base = ch * 32;
     uint32_t two[2] = {0, 0};
@@ -144,6 +141,104 @@ twobit_windows_kernel(const uint8_t *__restrict__ blob, const unsigned long long
       p = wend;
     }
     *reinterpret_cast<uint2 *>(lib2 + ch * 2) = make_uint2(two[0], two[1]);
+  }
+}
+
+// T0 C1 A2 G3 with the first base of a byte in its top bits  ->  A0 C1 G2 T3 with base i of the word
+// at bits 2i: reverse the four 2-bit fields of every byte, then recode (hi' = ~(hi ^ lo), lo' = ~hi)
+__device__ __forceinline__ uint32_t twobit_word_to_lib2(uint32_t x)
+{
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+  const uint32_t h = x & 0xaaaaaaaau, l = x & 0x55555555u;
+  return (~(h ^ (l << 1)) & 0xaaaaaaaau) | ((~h >> 1) & 0x55555555u);
+}
+
+// One thread produces 128 library bases (32 bytes of lib2, two 128-bit stores) from the 33 source
+// bytes that cover them, read as three aligned 128-bit loads; consecutive threads read and write
+// consecutive addresses. The twelve source words are recoded 16 bases at a time and funnel-shifted
+// to the library's alignment. Groups that are not inside one window (at most one per window
+// boundary, plus the tail) are only recorded here and decoded base by base by
+// twobit_boundary_kernel, so that no warp of this kernel waits for a slow lane.
+__global__ void __launch_bounds__(256)
+twobit_windows_kernel(const uint8_t *__restrict__ blob, const unsigned long long blob_bytes,
+                      const WindowDev *__restrict__ win, const int n_win,
+                      const unsigned long long total, uint32_t *__restrict__ lib2,
+                      const unsigned long long n_chunks, unsigned long long *__restrict__ slow_list,
+                      unsigned int *__restrict__ slow_count)
+{
+  const unsigned long long n_groups = (n_chunks + 3) / 4;
+  for (unsigned long long g = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+       g < n_groups; g += (unsigned long long) gridDim.x * blockDim.x)
+  {
+    const unsigned long long base = g * 128;
+    int lo = 0, hi = n_win - 1;
+    while (lo < hi)
+    {
+      const int mid = (lo + hi + 1) >> 1;
+      if (win[mid].dst <= base)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+    bool fast = false;
+    unsigned long long a0 = 0;
+    int bitoff = 0;
+    if (n_win > 0)
+    {
+      const WindowDev W = win[lo];
+      const unsigned long long sb = W.src_base + (base - W.dst);
+      const unsigned long long byte0 = W.src_byte + (sb >> 2);
+      a0 = byte0 & ~15ull;
+      bitoff = (int) (byte0 - a0) * 8 + 2 * (int) (sb & 3);
+      fast = (W.dst <= base) && (base + 128 <= W.dst + W.len) && (base + 128 <= total) &&
+             (a0 + 48 <= blob_bytes) && ((reinterpret_cast<unsigned long long>(blob) & 15ull) == 0);
+    }
+    if (fast)
+    {
+      uint32_t cw[12];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(blob + a0) + i);
+        cw[4 * i + 0] = twobit_word_to_lib2(v.x);
+        cw[4 * i + 1] = twobit_word_to_lib2(v.y);
+        cw[4 * i + 2] = twobit_word_to_lib2(v.z);
+        cw[4 * i + 3] = twobit_word_to_lib2(v.w);
+      }
+      const int k0 = bitoff >> 5, sh = bitoff & 31;   // k0 in 0..3
+      uint32_t t[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j)
+        t[j] = (k0 == 0) ? cw[j] : (k0 == 1) ? cw[j + 1] : (k0 == 2) ? cw[j + 2] : cw[j + 3];
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = __funnelshift_r(t[j], t[j + 1], sh);
+      uint4 *dst = reinterpret_cast<uint4 *>(lib2 + g * 8);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    else
+      slow_list[atomicAdd(slow_count, 1u)] = g;
+  }
+}
+
+// the groups twobit_windows_kernel left out: one thread per 32-base chunk
+__global__ void __launch_bounds__(128)
+twobit_boundary_kernel(const uint8_t *__restrict__ blob, const unsigned long long blob_bytes,
+                       const WindowDev *__restrict__ win, const int n_win,
+                       const unsigned long long total, uint32_t *__restrict__ lib2,
+                       const unsigned long long n_chunks, const unsigned long long *__restrict__ slow_list,
+                       const unsigned int *__restrict__ slow_count)
+{
+  const unsigned long long n = 4ull * *slow_count;
+  for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long) gridDim.x * blockDim.x)
+  {
+    const unsigned long long ch = slow_list[i >> 2] * 4 + (i & 3);
+    if (ch < n_chunks)
+      twobit_chunk_slow(blob, blob_bytes, win, n_win, total, lib2, ch);
   }
 }
 

@@ -377,11 +377,26 @@ extern "C" int ramcu_library_from_twobit(ramcu_ctx *c, const uint8_t *blob, uint
     CK(cudaMemcpyAsync(d_blob, blob, blob_bytes, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMallocAsync(&d_win, (size_t) std::max(n_windows, 1) * sizeof(WindowDev), c->stream));
     CK(cudaMemcpyAsync(d_win, windows, (size_t) n_windows * sizeof(WindowDev), cudaMemcpyHostToDevice, c->stream));
-    const unsigned long long want = (n_chunks + 255) / 256;
+    const unsigned long long want = ((n_chunks + 3) / 4 + 255) / 256;   // one thread per 128 bases
     const int grid = (int) std::min<unsigned long long>(want, (unsigned long long) c->sm_count * 16);
+    // groups of 128 bases that are not inside one window: at most one per window boundary + the tail
+    unsigned long long *d_slow = nullptr;
+    unsigned int *d_nslow = nullptr;
+    CK(cudaMallocAsync(&d_slow, ((size_t) n_windows + 4) * sizeof(unsigned long long), c->stream));
+    CK(cudaMallocAsync(&d_nslow, sizeof(unsigned int), c->stream));
+    CK(cudaMemsetAsync(d_nslow, 0, sizeof(unsigned int), c->stream));
     twobit_windows_kernel<<<grid, 256, 0, c->stream>>>(d_blob, blob_bytes, d_win, n_windows, total,
-                                                       lib->d_lib2, n_chunks);
+                                                       lib->d_lib2, n_chunks, d_slow, d_nslow);
     CK(cudaGetLastError());
+    {
+      const unsigned long long wantb = (4ull * ((unsigned long long) n_windows + 4) + 127) / 128;
+      const int gridb = (int) std::min<unsigned long long>(wantb, (unsigned long long) c->sm_count * 16);
+      twobit_boundary_kernel<<<gridb, 128, 0, c->stream>>>(d_blob, blob_bytes, d_win, n_windows, total,
+                                                           lib->d_lib2, n_chunks, d_slow, d_nslow);
+      CK(cudaGetLastError());
+    }
+    CK(cudaFreeAsync(d_slow, c->stream));
+    CK(cudaFreeAsync(d_nslow, c->stream));
     // positions past `total` inside the last chunk are N
     if (total & 31)
     {

@@ -29,6 +29,7 @@ struct uint2 { unsigned x, y; };
 struct dim3e { unsigned x, y, z; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 v = {x, y, z, w}; return v; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 v = {x, y}; return v; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
 
 struct EmulWarp
 {
@@ -98,6 +99,7 @@ static inline int __reduce_max_sync(unsigned, int v)
   return m;
 }
 static inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __sync_fetch_and_add(p, v); }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __sync_fetch_and_or(p, v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __sync_fetch_and_add(p, v); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }

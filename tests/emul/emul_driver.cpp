@@ -6,6 +6,7 @@
 #include <pthread.h>
 #include <stdio.h>
 #include <vector>
+#include <functional>
 
 #include "cuda_emul.h"
 #include "../../repeatafterme_b200/csrc/extend_kernel.cuh"
@@ -34,6 +35,8 @@ struct LaunchArgs
   const uint8_t *bytes;
   unsigned long long len, n_chunks;
   uint32_t *lib2, *libn;
+  // any other kernel, bound with its arguments
+  const std::function<void()> *gen;
 };
 
 static void *thread_main(void *p)
@@ -45,7 +48,9 @@ static void *thread_main(void *p)
   gridDim = {(unsigned) a->grid, 1, 1};
   emul_cta = a->cta;
   emul_warp = &a->cta->warps[a->tid >> 5];
-  if (a->fn)
+  if (a->gen)
+    (*a->gen)();
+  else if (a->fn)
     a->fn(a->fams, a->cta_fam, a->ticket);
   else
     a->pfn(a->bytes, a->len, a->lib2, a->libn, a->n_chunks);
@@ -256,4 +261,40 @@ extern "C" int emul_extend_paths(int C, int G, int WS, int threads, const uint8_
   return emul_extend_impl(C, G, WS, threads, seq, seq_len, direction, n_cores, cores, sc, pr, master_out,
                           ext_len_out, score_add_out, res, 0, nullptr, nullptr, nullptr, nullptr, path_out,
                           pbest_out, pidx_out);
+}
+
+// Same contract as the device part of ramcu_library_from_twobit() (include/ramcu.h): 2bit packed DNA
+// + window list -> lib2 words (twobit_windows_kernel + twobit_boundary_kernel). lib2_out holds
+// 2 * ceil(total / 32) words, zeroed by the caller.
+extern "C" int emul_twobit(const uint8_t *blob, unsigned long long blob_bytes, const ramcu_window_t *windows,
+                           int n_windows, unsigned long long total, uint32_t *lib2_out)
+{
+  static_assert(sizeof(ramcu_window_t) == sizeof(WindowDev), "window layout");
+  const WindowDev *win = reinterpret_cast<const WindowDev *>(windows);
+  const unsigned long long n_chunks = (total + 31) / 32;
+  // the fast path needs a 16-byte aligned blob with whole 16-byte loads readable
+  std::vector<uint8_t> store(blob_bytes + 64, 0);
+  uint8_t *ab = store.data() + ((16 - (reinterpret_cast<uintptr_t>(store.data()) & 15)) & 15);
+  memcpy(ab, blob, blob_bytes);
+  std::vector<unsigned long long> slow((size_t) n_windows + 4, 0);
+  unsigned int nslow = 0;
+  {
+    const std::function<void()> k = [&]() {
+      twobit_windows_kernel(ab, blob_bytes, win, n_windows, total, lib2_out, n_chunks, slow.data(), &nslow);
+    };
+    LaunchArgs a = {};
+    a.gen = &k;
+    if (launch(a, 3, 64))
+      return -1;
+  }
+  {
+    const std::function<void()> k = [&]() {
+      twobit_boundary_kernel(ab, blob_bytes, win, n_windows, total, lib2_out, n_chunks, slow.data(), &nslow);
+    };
+    LaunchArgs a = {};
+    a.gen = &k;
+    if (launch(a, 2, 32))
+      return -1;
+  }
+  return (int) nslow;
 }

@@ -105,3 +105,36 @@ def test_emul_outmat_config1(emul, oracle, cfg):
         assert a == b, f"line {i}"
     assert lines[-40:] == want["tail"]
     assert hashlib.sha256(("\n".join(lines) + "\n").encode()).hexdigest() == want["sha256"]
+
+
+@pytest.mark.parametrize("seed,n,flank,kw", [(301, 12, 700, dict(n_frac=0.01)), (302, 40, 90, dict(pad=3)),
+                                              (303, 3, 2500, dict()), (304, 25, 40, dict(pad=0))])
+def test_emul_twobit_decode(emul, seed, n, flank, kw):
+    """twobit_windows_kernel + twobit_boundary_kernel (2bit packed DNA of kentsrc/twoBitNew.c:571-582 ->
+    library words, 128 bases per thread with 128-bit loads, window-straddling groups base by base)
+    against a numpy decode of the same windows; windows of every length and alignment"""
+    import ctypes as C
+    fam = synth.make_family(seed, n, flank, 0.15, **kw)
+    blob, wins, ns, nl, total = synth.family_twobit_windows(fam)
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    wins = np.ascontiguousarray(wins, dtype=np.uint64)
+    n_chunks = (total + 31) // 32
+    lib2 = np.zeros(2 * n_chunks, dtype=np.uint32)
+    emul.lib.emul_twobit.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
+    nslow = emul.lib.emul_twobit(blob.ctypes.data, blob.size, wins.ctypes.data, len(wins), total, lib2.ctypes.data)
+    assert 0 <= nslow <= len(wins) + 4
+    if flank >= 700:
+        assert nslow < (total // 128) // 2   # most groups take the 128-bit path
+    # expected: the library bytes of the family (A0 C1 G2 T3; N -> code 0 + mask, masks are not this kernel's)
+    want = np.zeros(total, dtype=np.uint8)
+    for (dst, ln, src_byte, src_base) in wins.tolist():
+        idx = src_base + np.arange(ln)
+        byte = blob[src_byte + (idx >> 2)]
+        t = (byte >> (6 - 2 * (idx & 3)).astype(np.uint8)) & 3          # T0 C1 A2 G3
+        want[dst: dst + ln] = np.array([3, 1, 0, 2], dtype=np.uint8)[t]
+    i = np.arange(total)
+    got = (lib2[i >> 4] >> (2 * (i & 15)).astype(np.uint32)) & 3
+    assert np.array_equal(got.astype(np.uint8), want)
+    seq = np.asarray(fam.sequence)
+    known = seq <= 3
+    assert np.array_equal(want[known], seq[known])   # and that is the reference loader's byte per base
