@@ -327,32 +327,45 @@ def run_cuda(args):
 
     # ---- config-5 style batch: many independent families sharing the GPU (families/s) -------------
     fam_info = None
-    if args.families > 0 and world == 1:
+    fam_stats = None
+    if args.families > 0:
+        # BASELINE configs[4] shape: a seeded sample of the 2 000-family mix, `--families` per GPU, sharded by
+        # family over the ranks (longest-processing-time-first, no communication between ranks)
         specs = synth.config5_specs(5, 2000)
-        pick = np.random.default_rng(0).choice(len(specs), size=args.families, replace=False)
-        fams5 = [synth.family_from_spec(specs[i]) for i in sorted(pick)]
+        pick = sorted(np.random.default_rng(0).choice(len(specs), size=args.families * world, replace=False))
+        costs = [batch.family_cost(specs[i]["n"], specs[i]["params"]["bandwidth"], specs[i]["flank"]) for i in pick]
+        mine = batch.lpt_shard(costs, world)[rank]
+        fams5 = [synth.family_from_spec(specs[pick[i]]) for i in mine]
         batch.extend_families(rc, fams5)          # warm-up: first use of every tiling in the mix loads its code
         times5 = []
         for _ in range(3):
-            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
             res5 = batch.extend_families(rc, fams5)
             torch.cuda.synchronize()
             times5.append(time.perf_counter() - t0)
-        dt = float(np.median(times5))
         cu5 = sum(x.cell_updates for x in res5)
-        fam_info = {"n_families": len(fams5), "instances": int(sum(f.n for f in fams5)),
-                    "families_per_s": round(len(fams5) / dt, 2), "gcups_e2e": round(cu5 / dt / 1e9, 1),
-                    "seconds": round(dt, 3), "seconds_all_runs": [round(x, 3) for x in times5],
-                    "what": "seeded sample of the BASELINE configs[4] family mix (N 100-10k log-uniform, "
-                            "bandwidth 20-100, flank 0.5-5 kb), host buffers in / host results out; median of three "
-                            "runs after one warm-up run"}
+        fam_stats = (float(np.median(times5)), float(len(fams5)), float(cu5), float(sum(f.n for f in fams5)))
 
     for j in jobs:
         rc.job_free(j)
     rc.free_library(lib)
 
     # ---- max over ranks -------------------------------------------------------------------------
+    if fam_stats is not None:
+        fs = torch.tensor(fam_stats, dtype=torch.float64, device="cuda")
+        if world > 1:
+            fmx = fs.clone()
+            dist.all_reduce(fmx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(fs, op=dist.ReduceOp.SUM)
+            fs[0] = fmx[0]
+        dt5, nf5, cu5, ni5 = (float(x) for x in fs)
+        fam_info = {"n_families": int(nf5), "instances": int(ni5), "families_per_s": round(nf5 / dt5, 2),
+                    "gcups_e2e": round(cu5 / dt5 / 1e9, 1), "seconds": round(dt5, 3),
+                    "what": "seeded sample of the BASELINE configs[4] family mix (N 100-10k log-uniform, "
+                            "bandwidth 20-100, flank 0.5-5 kb), %d families per GPU sharded by family (LPT) over "
+                            "the ranks, host buffers in / host results out; per rank the median of three runs "
+                            "after one warm-up run, max over ranks" % args.families}
     stats = torch.tensor([dev_ms, e2e_s, cu_step, e2e2_s], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
