@@ -985,24 +985,49 @@ extern "C" int ramcu_job_create_pair(ramcu_ctx *c, ramcu_library *lib, int n_cor
                                    pr->concurrent_instances, pr->cta_thread_limit, &solo, &nb);
     if (k0)
     {
-      // same lanes per instance as the family alone; full registers if both passes fit the
-      // device side by side, else the tiling compiled for half the registers
+      // same lanes per instance as the family alone, with full registers if both passes fit the
+      // device side by side, else the tiling compiled for half the registers; failing that, the
+      // cheapest other half-register tiling of this band (by the single-family cost model) that fits
+      auto fits = [&](int G, int maxt, double *cost) -> bool {
+        Plan sr, sl;
+        int br = 0, bl = 0;
+        const KernelCfg *kr = pick_cfg(c, pr->bandwidth, n_r, G, pr->concurrent_instances, maxt, &sr, &br);
+        const KernelCfg *kl = pick_cfg(c, pr->bandwidth, n_l, G, pr->concurrent_instances, maxt, &sl, &bl);
+        if (!kr || kr != kl || kr->maxt != maxt || kr->G != G || br <= 0 || bl <= 0)
+          return false;
+        if ((long long) br + bl > (long long) ctas_per_sm(kr, kBatchThreads) * c->sm_count)
+          return false;
+        if (cost)
+          *cost = solo_cost(c, kr, std::max(n_r, n_l), n_r >= n_l ? sr : sl);
+        return true;
+      };
       const int tries[2] = {k0->maxt, 512};
       for (int t = 0; t < 2 && !together; ++t)
       {
         if (pr->cta_thread_limit > 0 && tries[t] != pr->cta_thread_limit)
           continue;
-        Plan sr, sl;
-        int br = 0, bl = 0;
-        const KernelCfg *kr = pick_cfg(c, pr->bandwidth, n_r, k0->G, pr->concurrent_instances, tries[t], &sr, &br);
-        const KernelCfg *kl = pick_cfg(c, pr->bandwidth, n_l, k0->G, pr->concurrent_instances, tries[t], &sl, &bl);
-        if (!kr || kr != kl || kr->maxt != tries[t] || br <= 0 || bl <= 0)
-          continue;
-        if ((long long) br + bl > (long long) ctas_per_sm(kr, kBatchThreads) * c->sm_count)
+        if (!fits(k0->G, tries[t], nullptr))
           continue;
         p.lanes_per_instance = k0->G;
         p.cta_thread_limit = tries[t];
         together = true;
+      }
+      if (!together && pr->lanes_per_instance <= 0 && (pr->cta_thread_limit <= 0 || pr->cta_thread_limit == 512))
+      {
+        double best_cost = 0;
+        for (int G = 1; G <= 32; ++G)
+        {
+          double cost = 0;
+          if (G == k0->G || !fits(G, 512, &cost))
+            continue;
+          if (!together || cost < best_cost)
+          {
+            best_cost = cost;
+            p.lanes_per_instance = G;
+            p.cta_thread_limit = 512;
+            together = true;
+          }
+        }
       }
     }
   }
