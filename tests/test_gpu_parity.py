@@ -158,6 +158,20 @@ def test_batch_equals_individual_runs(ramcu, oracle):
             support.compare_extend(want, got, f"batch dir={d}")
 
 
+def test_batch_with_and_without_between_passes_hook(ramcu):
+    """extend_families: all passes of all families in one batch (no hook) == right batch, hook, left
+    batch (the form a caller with an overlap-avoidance step uses)"""
+    specs = synth.config5_specs(7, 6)
+    fams = [synth.family_from_spec(dict(s, n=max(20, s["n"] // 30), flank=max(60, s["flank"] // 10))) for s in specs]
+    seen = []
+    a = batch.extend_families(ramcu, fams)
+    b = batch.extend_families(ramcu, fams, between_passes=lambda f, right: seen.append(right["extended_bp"]))
+    assert len(seen) == len(fams)
+    for x, y in zip(a, b):
+        support.compare_extend(x.right, y.right, "hook vs no hook, right")
+        support.compare_extend(x.left, y.left, "hook vs no hook, left")
+
+
 @pytest.mark.parametrize("seed,n,flank,B,matrix,kw", [
     (111, 300, 300, 40, "14p43g", dict(one_sided_frac=0.2, n_frac=0.005)),   # both passes in few CTAs
     (112, 90, 250, 14, "20p43g", dict()),                                    # one CTA per pass
