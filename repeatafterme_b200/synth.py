@@ -280,3 +280,29 @@ def family_twobit_windows(fam: Family):
         dst += hi - lo
     return (np.concatenate(blobs), np.array(wins, dtype=np.uint64), np.array(n_start, dtype=np.uint64),
             np.array(n_len, dtype=np.uint64), dst)
+
+
+def config5_parity_sample(specs=None, seed: int = 11):
+    """Seeded, stratified sample of the config-5 family mix used to pin parity at FULL size against
+    the reference (tests/golden/flat_config5_sample.npz): for every bandwidth one family from each
+    of four size strata (N < 300, < 1000, < 3500, >= 3500; families above 3e10 cell updates are left
+    out to bound the reference's CPU time) plus, for bandwidth 40 and 100, the cheapest family with
+    N >= 5000 that is not picked already. Returns indices into `specs`."""
+    specs = specs if specs is not None else config5_specs()
+    rng = np.random.default_rng(seed)
+
+    def cu(i):
+        return specs[i]["n"] * (2 * specs[i]["params"]["bandwidth"] + 1) * (specs[i]["flank"] + 100) * 8.0
+
+    edges = [0, 300, 1000, 3500, 1 << 30]
+    pick = []
+    for bw in (20, 40, 60, 80, 100):
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            cell = [i for i, s in enumerate(specs)
+                    if s["params"]["bandwidth"] == bw and lo <= s["n"] < hi and cu(i) <= 3e10]
+            pick.append(int(cell[int(rng.integers(0, len(cell)))]))
+    for bw in (40, 100):
+        big = sorted((i for i, s in enumerate(specs)
+                      if s["n"] >= 5000 and s["params"]["bandwidth"] == bw and i not in pick), key=cu)
+        pick.append(big[0])
+    return sorted(pick)

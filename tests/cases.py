@@ -249,3 +249,55 @@ def parse_stk(path):
         rows.append(dict(chrom=m.group(1), start=int(m.group(2)) - 1, end=int(m.group(3)),
                          left=left, right=right, orient=m.group(4), seq=aln.replace(".", "").upper()))
     return rows
+
+
+# ---------------------------------------------------------------------------------------------
+# Full-size cases (tests/golden/make_golden_full.py): inputs come from seeds, the fixtures hold only
+# the reference's outputs and the sha256 of the regenerated inputs.
+# ---------------------------------------------------------------------------------------------
+CONFIG4 = dict(bandwidth=40, matrix="14p43g", minimprovement=30, cappenalty=-90, L=20000, when_to_stop=100)
+
+WIDE_CASES = {
+    # bandwidth 500 is what util/davidExtendConsRAM.pl:248 passes; 511 the widest register-tiled band
+    "b500": dict(seed=51, n=150, flank=700, div=0.15, params=dict(CONFIG4, bandwidth=500)),
+    "b511": dict(seed=52, n=60, flank=400, div=0.20, one_sided=0.2,
+                 params=dict(CONFIG4, bandwidth=511, matrix="20p43g", minimprovement=27)),
+    # a family that spans far more than 40 CTAs at bandwidth 100 (RED exchange path)
+    "b100_many_ctas": dict(seed=53, n=3000, flank=800, div=0.12, one_sided=0.1, params=dict(CONFIG4, bandwidth=100)),
+}
+
+
+def _cu(n, bandwidth, flank):
+    return n * (2 * bandwidth + 1) * (flank + 100) * 8.0
+
+
+def _config4_keys():
+    return [("seed4", _cu(10000, 40, 5000))]
+
+
+def _config5_keys():
+    specs = synth.config5_specs()
+    return [(i, _cu(specs[i]["n"], specs[i]["params"]["bandwidth"], specs[i]["flank"]))
+            for i in synth.config5_parity_sample(specs)]
+
+
+def _wide_keys():
+    return [(k, _cu(v["n"], v["params"]["bandwidth"], v["flank"])) for k, v in WIDE_CASES.items()]
+
+
+FULL_CASES = {"config4_full": _config4_keys, "config5_sample": _config5_keys, "wide_bands": _wide_keys}
+
+
+def full_case_family(group, key):
+    """the synth.Family (with .params) of one full-size case"""
+    if group == "config4_full":
+        fam = synth.make_family(4, 10000, 5000, 0.15)      # exactly bench.py's rank-0 family
+        fam.params = dict(CONFIG4)
+        return fam
+    if group == "config5_sample":
+        return synth.family_from_spec(synth.config5_specs()[int(key)])
+    if group == "wide_bands":
+        c = WIDE_CASES[str(key)]
+        return synth.make_family(c["seed"], c["n"], c["flank"], c["div"], one_sided_frac=c.get("one_sided", 0.0),
+                                 params=c["params"])
+    raise KeyError(group)
