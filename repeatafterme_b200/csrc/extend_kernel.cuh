@@ -5,20 +5,31 @@
 //
 // Mapping:
 //   * an MSA instance's band of W = 2B+1 cells is split into G contiguous segments of C cells;
-//     one lane owns one segment (G lanes per instance, G in {1,2,4,..,32}, G*C >= W). The two
-//     DP states (sub/gap) of the committed previous row live in registers: Sp[C], Gp[C].
-//   * all four candidate consensus bases are evaluated in one sweep over the segment; per
-//     candidate only the running (S,G) pair and the row best are kept.
-//   * the in-row insertion chain G[o] = max(X[o], G[o-1]+ge) is a max-plus prefix scan: serial
-//     inside a lane, Hillis-Steele over the G lanes with __shfl_up_sync (decay C*ge per lane).
-//   * per-candidate best scores are butterfly-reduced over the G lanes (__shfl_xor_sync), capped
-//     (max(best,0,high+CAPPENALTY)), summed over the warp (__reduce_add_sync), the CTA (shared
-//     memory) and, for families spanning several CTAs, over the grid with a data+flag ("LL")
-//     exchange through L2 - no host round trip and no cooperative launch per column.
-//   * the chosen base's row is then re-materialised in place (the reference's "5th pass",
-//     ram_extend.c:1105-1150) with the true carries, together with the first-max column index.
+//     one lane owns one segment (G lanes per instance, any G in 1..32, G*C >= W).
+//   * row state in registers, per cell, in the form the NEXT row consumes it:
+//         P[k] = max(sub, gap)                  of the committed row      (bnw_extend.c:1012-1018)
+//         D[k] = max(sub + go + ge, gap + ge)   of the cell to the RIGHT  (the deletion term of
+//                                               bnw_extend.c:892-905 for cell k of the next row;
+//                                               the same expression is the insertion term of
+//                                               bnw_extend.c:972-985 for the cell right of it)
+//   * sweep (all four candidate consensus bases, no dependency between cells): with non-positive
+//     gap penalties the insertion term never exceeds the cell left of it, so the row best is
+//         best_a = max_k max(P[k] + m[a][base_k], D[k])
+//     exactly -- one fused add+max per cell and candidate, no insertion chain, no cross-lane scan.
+//   * per-candidate bests are reduced over the G lanes, capped (max(best,0,high+CAPPENALTY)),
+//     summed over the warp (__reduce_add_sync), the CTA (shared memory) and, for families
+//     spanning several CTAs, over the grid with a data+flag exchange through L2 - no host
+//     round trip and no cooperative launch per column.
+//   * commit: only the chosen base's row is materialised (the reference's "5th pass",
+//     ram_extend.c:1105-1150). The insertion chain H[k] = max(y[k], H[k-1] + ge) is serial inside
+//     a lane; across the G lanes the lane aggregates are combined by a max-plus prefix scan
+//     (__shfl_up_sync, decay C*ge per lane) and the true carry is folded in afterwards
+//     (P[k] = max(P[k], carry + k*ge), H[k] = max(H[k], carry + (k+1)*ge)), together with the
+//     first-max column index.
 //   * integer max-plus only: no tensor cores. Sentinels (-1000000000 / -987654321) and the
-//     edge rule are the reference's, so every cell value is bit-identical.
+//     edge rule are the reference's, so every cell value is bit-identical. Rows whose band hangs
+//     over a sequence bound (or runtime-width bands, or positive gap penalties) take an exact
+//     per-cell predicated path with an (aggregate, transfer) scan.
 #pragma once
 #ifdef RAMCU_EMUL
 #include "cuda_emul.h"   // tests/emul: CPU lock-step emulation of the SIMT primitives (tests only)
@@ -172,142 +183,165 @@ __device__ __forceinline__ int win_byte(const uint32_t w, const int j)
 #endif
 }
 
-// One pass over the lane's C cells for NC candidates (NC = 4: all bases; NC = 1: base a0).
-//   SLOW   : per-cell bounds predicates (exact out-of-bounds / edge / dead-cell semantics)
-//   COMMIT : write the new row into Sp/Gp and track the first cell whose score == bestv
-//   BEST   : accumulate the row best per candidate
-//   PDOUT  : leave P = max(Sp,Gp) and D (the two candidate-independent terms of the row) in Sp/Gp
-//            in place of the previous row, which this pass has finished reading at that point
-//   PDIN   : Sp/Gp already hold P and D (the commit after a PDOUT sweep recomputes neither)
-// sin/gin  : S and G of the cell left of this lane's first cell (current row)
-// gout     : G of this lane's last cell
-template <int C, int G, int WS, bool SLOW, int NC, bool COMMIT, bool BEST, bool PDIN, bool PDOUT>
-__device__ __forceinline__ void band_pass(int (&Sp)[C], int (&Gp)[C], const int SpN,
-                                          const int GpN, const uint32_t *win, const char *lutb,
-                                          const int a0, const int go, const int ge,
-                                          const int (&sin)[NC], const int (&gin)[NC],
-                                          int (&gout)[NC], int (&best)[NC], const int bestv,
-                                          int &idx, const int gl, const int W, const int B,
-                                          const int r, const int tmin, const int tmax)
+// ---------------------------------------------------------------------------------------------
+// flank feed: the base that enters the band at its high end, 16 band positions per load
+// ---------------------------------------------------------------------------------------------
+// eight 2-bit fields (low 16 bits) -> bits 0..1 of eight nibbles
+__device__ __forceinline__ uint32_t spread2to4(uint32_t x)
+{
+  x &= 0xffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  return x;
+}
+// eight bits (low 8 bits) -> bit 0 of eight nibbles
+__device__ __forceinline__ uint32_t spread1to4(uint32_t x)
+{
+  x &= 0xffu;
+  x = (x | (x << 12)) & 0x000f000fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x;
+}
+
+// Codes (0..3 base, complemented for reverse cores; 4 = N; 5 = outside the sequence bounds) of
+// band positions t0 .. t0+15 of an instance as sixteen nibbles (nlo: t0..t0+7, nhi: t0+8..t0+15).
+// Two 32-bit words of each library array are read per call instead of one word per row.
+__device__ __forceinline__ void feed16(const uint32_t *__restrict__ lib2, const uint32_t *__restrict__ libn,
+                                       const long long start, const int sgn, const int comp,
+                                       const int tmin, const int tmax, const int t0, uint32_t &nlo,
+                                       uint32_t &nhi)
+{
+  const int lo = min(max(tmin - t0, 0), 16), hi = min(max(tmax - t0 + 1, 0), 16);
+  const uint32_t inb = (hi > lo) ? ((0xffffu >> (16 - hi)) & ~((1u << lo) - 1u)) : 0u;
+  uint32_t codes = 0, nm = 0;
+  if (inb)
+  {
+    // lowest sequence index of the group; every in-bounds position lies inside the library
+    // (flatten_cores clips the bounds), the arrays are padded by four words on both sides
+    const long long p = (sgn > 0) ? start + t0 : start - t0 - 15;
+    const long long w2 = p >> 4, wn = p >> 5;
+    codes = __funnelshift_r(__ldg(lib2 + w2), __ldg(lib2 + w2 + 1), 2 * (int) (p & 15));
+    nm = __funnelshift_r(__ldg(libn + wn), __ldg(libn + wn + 1), (int) (p & 31)) & 0xffffu;
+    if (sgn < 0)
+    {
+      codes = __brev(codes);
+      codes = ((codes >> 1) & 0x55555555u) | ((codes & 0x55555555u) << 1);
+      nm = __brev(nm) >> 16;
+    }
+    if (comp)
+      codes = ~codes;
+  }
+  const uint32_t ob = ~inb;
+  uint32_t c0 = spread2to4(codes), c1 = spread2to4(codes >> 16);
+  const uint32_t n0 = spread1to4(nm), n1 = spread1to4(nm >> 8);
+  const uint32_t o0 = spread1to4(ob), o1 = spread1to4(ob >> 8);
+  c0 = (c0 & ~(n0 * 15u)) | (n0 << 2);
+  c1 = (c1 & ~(n1 * 15u)) | (n1 << 2);
+  nlo = (c0 & ~(o0 * 15u)) | (o0 * 5u);
+  nhi = (c1 & ~(o1 * 15u)) | (o1 * 5u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact per-cell row pass (rows whose band hangs over a sequence bound, runtime band widths,
+// positive gap penalties, debug output)
+// ---------------------------------------------------------------------------------------------
+struct RowDbg
+{
+  int *rows;             // [n_ext][W][2] of this row (or NULL)
+  unsigned char *path;   // [n_ext][W] of this row (or NULL)
+  int inst;
+  bool valid;
+};
+
+// One pass over the lane's C cells for candidate base a, bnw_extend.c:800-1018 cell by cell:
+//   in bounds : S = P + m[a][base], G = max(D, H of the cell to the left)      (D = NEG at offset +B,
+//               H(left) = NEG at offset -B)
+//   otherwise : S = G = edge value (offset < 0 && row < bandwidth) or the out-of-bounds sentinel
+//   cell = max(S, G), H = max(S + go + ge, G + ge)
+// hin is H of the cell left of the lane. FINAL: hin is the true value, `best` accumulates the row
+// best over the real cells; COMMIT additionally writes the new state (P in place, H of cell k into
+// the D slot of cell k-1, H of cell 0 to h0), the first cell equal to bestv and the debug output.
+// Returns H of the lane's last cell.
+template <int C, bool FINAL, bool COMMIT>
+__device__ __forceinline__ int exact_pass(int (&Pp)[C], int (&Dd)[C], const uint32_t *win, const char *lutb,
+                                          const int a, const int go, const int ge, const int hin,
+                                          const int gl, const int W, const int B, const int r,
+                                          const int tmin, const int tmax, int &best, const int bestv,
+                                          int &idx, int &h0, const RowDbg &dbg)
 {
   const int goe = go + ge;
-  const bool is_last = (gl == G - 1);
-  const int Wc = WS ? WS : W;
-  const int kR = Wc - 1 - (G - 1) * C;   // last real cell of the last lane (static if WS != 0)
-  const int edge = go + (r + 1) * ge;    // bnw_extend.c:992
-  const int tbase = r - B + gl * C;      // band position t of cell 0
-  int sprev[NC], gprev[NC];
-#pragma unroll
-  for (int a = 0; a < NC; ++a)
-  {
-    sprev[a] = sin[a];
-    gprev[a] = gin[a];
-  }
-  static_assert(!(PDIN && PDOUT) && !(PDOUT && COMMIT), "P/D hand-over is sweep -> commit");
+  const int edge = go + (r + 1) * ge;   // bnw_extend.c:992
+  const int tbase = r - B + gl * C;
+  int hprev = hin;
   if (COMMIT)
     idx = kBig;
-  unsigned hits = 0;   // COMMIT, C <= 32: bit k set when cell k holds the row best
-
 #pragma unroll
   for (int k = 0; k < C; ++k)
   {
-    int P, D;
-    if (PDIN)
-    {
-      P = Sp[k];
-      D = Gp[k];
-    }
-    else
-    {
-      const int sN = (k + 1 < C) ? Sp[(k + 1 < C) ? k + 1 : 0] : SpN;
-      const int gN = (k + 1 < C) ? Gp[(k + 1 < C) ? k + 1 : 0] : GpN;
-      P = imax(Sp[k], Gp[k]);
-      D = imax(sN + goe, gN + ge);
-    }
-    const int byte = win_byte(win[k >> 2], k & 3);
-    bool real = true, inb = true;
-    int E = 0;
-    if (SLOW)
-    {
-      const int K = gl * C + k;
-      real = K < Wc;
-      if (K >= Wc - 1)
-        D = kNeg;                          // offset == bandwidth: no deletion (bnw_extend.c:892)
-      const int t = tbase + k;
-      inb = real && (t >= tmin) && (t <= tmax);
-      E = (K < B && r < B) ? edge : kOob;  // bnw_extend.c:990-1002
-    }
-    else
-    {
-      if (k == kR)
-        D = is_last ? kNeg : D;
-      if (k > kR)
-        real = !is_last;
-    }
-    if (PDOUT)
-    {
-      Sp[k] = P;
-      Gp[k] = D;
-    }
-    int mv[NC];
-    if constexpr (NC == 4)
-    {
-      const int4 m4 = *reinterpret_cast<const int4 *>(lutb + byte);
-      mv[0] = m4.x;
-      mv[1] = m4.y;
-      mv[2] = m4.z;
-      mv[3] = m4.w;
-    }
-    else
-    {
-      mv[0] = *reinterpret_cast<const int *>(lutb + byte + 4 * a0);
-    }
-    int s0 = 0, g0 = 0;
-#pragma unroll
-    for (int a = 0; a < NC; ++a)
-    {
-      int S = P + mv[a];
-      int Gv = imax3(D, sprev[a] + goe, gprev[a] + ge);
-      if (SLOW)
-      {
-        S = inb ? S : E;
-        Gv = inb ? Gv : E;
-      }
-      if (BEST)
-      {
-        const int nb = imax3(best[a], S, Gv);
-        if (SLOW || k > kR)
-          best[a] = real ? nb : best[a];
-        else
-          best[a] = nb;
-      }
-      sprev[a] = S;
-      gprev[a] = Gv;
-      if (a == 0)
-      {
-        s0 = S;
-        g0 = Gv;
-      }
-    }
+    const int K = gl * C + k;
+    const bool real = K < W;
+    const int t = tbase + k;
+    const bool inb = real && (t >= tmin) && (t <= tmax);
+    const int E = (K < B && r < B) ? edge : kOob;   // bnw_extend.c:990-1002
+    const int Dk = (K >= W - 1) ? kNeg : Dd[k];     // offset == bandwidth: no deletion (:892)
+    const int m = *reinterpret_cast<const int *>(lutb + win_byte(win[k >> 2], k & 3) + 4 * a);
+    const int S = inb ? Pp[k] + m : E;
+    const int Gv = inb ? imax(Dk, hprev) : E;
+    const int pn = imax(S, Gv);
+    const int hn = imax(S + goe, Gv + ge);
+    if (FINAL)
+      best = real ? imax(best, pn) : best;
     if (COMMIT)
     {
-      Sp[k] = s0;
-      Gp[k] = g0;
-      const bool hit = (imax(s0, g0) == bestv) && real;
-      if constexpr (C <= 32)
+      idx = min(idx, (real && pn == bestv) ? k : kBig);
+      if (dbg.valid && real)
       {
-        if (hit)
-          hits |= 1u << k;
+        if (dbg.rows != nullptr)
+        {
+          int *o = dbg.rows + ((size_t) dbg.inst * W + K) * 2;
+          o[0] = S;
+          o[1] = Gv;
+        }
+        if (dbg.path != nullptr)   // sub == cell -> substitution, else del == cell -> deletion, else
+                                   // insertion (bnw_extend.c:1036-1041); out of bounds all three are equal
+          dbg.path[(size_t) dbg.inst * W + K] = (unsigned char) ((S == pn) ? 0 : (inb && Dk == pn) ? 1 : 2);
       }
+      Pp[k] = real ? pn : kNegInf;
+      if (k == 0)
+        h0 = hn;
       else
-        idx = min(idx, hit ? k : kBig);
+        Dd[k - 1] = hn;
+    }
+    hprev = hn;
+  }
+  return hprev;
+}
+
+// True H of the cell left of each lane from the lanes' local aggregates: an (aggregate, transfer)
+// max-plus scan over the G lanes of an instance. `agg` = H of the lane's last cell computed with no
+// carry-in; `open` = every cell of the lane is an in-bounds band cell (an out-of-bounds cell restarts
+// the chain, bnw_extend.c:988-1003, so nothing travels through such a lane).
+template <int C, int G>
+__device__ __forceinline__ int carry_scan_exact(int agg, const bool open, const int ge, const int gl)
+{
+  if (G == 1)
+    return kNeg;
+  int T = open ? C * ge : kNegInf;
+#pragma unroll
+  for (int d = 1; d < G; d <<= 1)
+  {
+    const int Tu = __shfl_up_sync(kFull, T, d);
+    const int up = __shfl_up_sync(kFull, agg, d);
+    if (gl >= d)
+    {
+      agg = imax(agg, imax(up, kNegInf) + T);
+      T = imax(T + Tu, kNegInf);
     }
   }
-  if constexpr (COMMIT && C <= 32)
-    idx = hits ? (__ffs((int) hits) - 1) : kBig;
-#pragma unroll
-  for (int a = 0; a < NC; ++a)
-    gout[a] = gprev[a];
+  const int cin = __shfl_up_sync(kFull, agg, 1);
+  return (gl == 0) ? kNeg : cin;   // offset == -bandwidth: no insertion (bnw_extend.c:972)
 }
 
 // Grid-level exchange of the four per-candidate column sums between the CTAs of a family.
@@ -432,6 +466,9 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   constexpr int IPW = 32 / G;   // instances per warp (lanes IPW*G..31 are spare when 32 % G != 0)
   static_assert(WS == 0 || ((G - 1) * C < WS && WS <= G * C), "band does not tile into G x C");
   constexpr int CW = (C + 3) / 4;
+  constexpr int HW = (C + 31) / 32;
+  // static band: index of the last real cell inside the last lane
+  constexpr int kR = WS ? WS - 1 - (G - 1) * C : C - 1;
 
   RAMCU_SHARED_STRUCT(SharedBlk, sh);
   int4 (&s_lut)[8] = sh.lut;
@@ -463,13 +500,13 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   const int B = F->B, W = WS ? WS : F->W;
   const int go = F->go, ge = F->ge, goe = go + ge, cap = F->cap, minimp = F->minimp;
   const int L = F->L, stop = F->stop, n_ext = F->n_ext, n_ctas = F->n_ctas;
-  // fast path: non-positive gaps (the carry peaks at a lane's first cell) of modest size (the scan
-  // adds kNegInf to travelling scores, see below)
-  const bool gaps_ok = (go <= 0) && (ge <= 0) && (go >= -100000) && ((long long) ge * (2 * F->B + 1) >= -(1 << 20));
+  // non-positive gap penalties: the insertion term of a cell never exceeds the cell left of it, so
+  // the row best needs no insertion chain (sweep) and a carry can only raise a prefix of a lane
+  const bool gaps_ok = (go <= 0) && (ge <= 0);
   const unsigned char *forced = F->forced;
   int *dbg_rows = F->dbg_rows;
-  const bool dbg_any = (F->dbg_rows != nullptr) || (F->dbg_best != nullptr);
   unsigned char *dbg_path = F->dbg_path;
+  const bool dbg_on = (dbg_rows != nullptr) || (dbg_path != nullptr);
 
   // balanced partition of the family's instances over its CTAs (n_ctas <= n_ext)
   const int first = (int) ((long long) cta_in_fam * n_ext / n_ctas);
@@ -480,146 +517,117 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   const InstDev I = F->inst[inst];
   const uint32_t *lib2 = F->lib2, *libn = F->libn;
   const int tmin = I.tmin, tmax = I.tmax;
+  const int K0 = gl * C;
 
-  int Sp[C], Gp[C];
+  // row state (see the header): boundary row S = G = (o == 0 ? 0 : |o| * ge + go), ram_extend.c:909-946
+  int Pp[C], Dd[C];
   uint32_t win[CW];
 #pragma unroll
   for (int i = 0; i < CW; ++i)
     win[i] = 0;
+  int maxD = kNeg;
 #pragma unroll
   for (int k = 0; k < C; ++k)
   {
-    const int o = gl * C + k - B;
-    const int v = (o == 0) ? 0 : abs(o) * ge + go;   // boundary row, ram_extend.c:909-946
-    Sp[k] = v;
-    Gp[k] = v;
+    const int K = K0 + k;
+    const int o = K - B;
+    const int v = (o == 0) ? 0 : abs(o) * ge + go;
+    const int v1 = (o + 1 == 0) ? 0 : abs(o + 1) * ge + go;
+    Pp[k] = (K < W) ? v : kNegInf;
+    Dd[k] = (K < W - 1) ? imax(v1 + goe, v1 + ge) : (K == W - 1) ? kNeg : kNegInf;
+    maxD = imax(maxD, Dd[k]);
     const int code = fetch_code(lib2, libn, I.start, I.sgn, I.comp, tmin, tmax, o);
     win[k >> 2] |= (uint32_t) (code << 4) << (8 * (k & 3));
   }
 
-  const int nreal = min(max(W - gl * C, 0), C);   // real (in-band) cells of this lane
+  const int nreal = min(max(W - K0, 0), C);   // real (in-band) cells of this lane
+  // rows in which every lane of this warp has its whole segment inside the sequence bounds, and
+  // the first row from which every band of the warp has left its window for good
+  const int r_fast_lo = __reduce_max_sync(kFull, tmin + B - K0);
+  const int r_fast_hi = __reduce_min_sync(kFull, tmax + B - K0 - nreal + 1);
+  const int r_dead = max(__reduce_max_sync(kFull, tmax) + B + 1, B);
+  const bool use_fast = (WS != 0) && gaps_ok && !dbg_on;
+
 #ifndef RAMCU_EMUL
   const long long t_begin = F->dbg_wait ? clock64() : 0;
 #endif
   int high = 0, pos = 0, thigh = 0, tpos = 0;   // ram_extend.c:900-914
   int max_row = -1, max_ext = 0, stop_row = -1;
+  uint32_t nib_lo = 0, nib_hi = 0;   // codes of the next band positions entering at the high end
   int r = 0;
 
   for (r = 0; r < L; ++r)
   {
     const int par = r & 1;
-    // base entering the band at its high end for the next row
-    int newc = 0;
-    if (is_last)
-      newc = fetch_code(lib2, libn, I.start, I.sgn, I.comp, tmin, tmax, r - B + G * C);
+    if ((r & 15) == 0 && is_last)
+      feed16(lib2, libn, I.start, I.sgn, I.comp, tmin, tmax, r - B + G * C, nib_lo, nib_hi);
 
-    const int tfirst = r - B + gl * C;
-    const bool lane_ok = (tfirst >= tmin) && (tfirst + nreal - 1 <= tmax);
-    const bool dead = (r - B > tmax) && (r >= B);   // every cell out of bounds, for good
-    const bool alldead = (dbg_rows == nullptr) && (dbg_path == nullptr) && __all_sync(kFull, dead);
-    const bool fast = (WS != 0) && gaps_ok && __all_sync(kFull, lane_ok);
+    const bool fast = use_fast && (r >= r_fast_lo) && (r <= r_fast_hi);
+    const bool alldead = !dbg_on && (r >= r_dead);   // every cell out of bounds, for good
 
     int best[4] = {kOob, kOob, kOob, kOob};
-    int sin4[4] = {0, 0, 0, 0}, carry[4] = {0, 0, 0, 0};
-    int SpN = 0, GpN = 0;
-    int idx_dummy = 0;
 
+    // ---- sweep: row best of every candidate base ---------------------------------------------
     if (!alldead)
     {
-      if (G > 1)
-      {
-        SpN = __shfl_down_sync(kFull, Sp[0], 1);
-        GpN = __shfl_down_sync(kFull, Gp[0], 1);
-      }
-      // S of this lane's last cell for the four candidates -> left input of the next lane
-      {
-        const int byte = win_byte(win[(C - 1) >> 2], (C - 1) & 3);
-        const int4 m4 = *reinterpret_cast<const int4 *>(lutb + byte);
-        const int P = imax(Sp[C - 1], Gp[C - 1]);
-        int sl[4] = {P + m4.x, P + m4.y, P + m4.z, P + m4.w};
-        if (!fast)
-        {
-          const int K = gl * C + C - 1;
-          const int t = tfirst + C - 1;
-          const bool inb = (K < W) && (t >= tmin) && (t <= tmax);
-          const int E = (K < B && r < B) ? (go + (r + 1) * ge) : kOob;
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
-            sl[a] = inb ? sl[a] : E;
+      for (int a = 0; a < 4; ++a)
+        best[a] = kNeg;   // bnw_extend.c:760
+      if (fast)
+      {
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+        {
+          const int4 m4 = *reinterpret_cast<const int4 *>(lutb + win_byte(win[k >> 2], k & 3));
+          best[0] = imax(best[0], Pp[k] + m4.x);
+          best[1] = imax(best[1], Pp[k] + m4.y);
+          best[2] = imax(best[2], Pp[k] + m4.z);
+          best[3] = imax(best[3], Pp[k] + m4.w);
         }
 #pragma unroll
         for (int a = 0; a < 4; ++a)
-        {
-          const int up = (G > 1) ? __shfl_up_sync(kFull, sl[a], 1) : 0;
-          sin4[a] = (gl == 0) ? (kNeg - goe) : up;   // offset == -bandwidth: no insertion (972)
-        }
+          best[a] = imax(best[a], maxD);
       }
-      int gin[4], agg[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
+      else if (gaps_ok)
       {
-        gin[a] = (gl == 0) ? (kNeg - ge) : kNegInf;
-        best[a] = kNeg;
-      }
-      if (fast)
-      {
-        band_pass<C, G, WS, false, 4, false, true, false, true>(Sp, Gp, SpN, GpN, win, lutb, 0, go, ge, sin4,
-                                                   gin, agg, best, 0, idx_dummy, gl, W, B, r,
-                                                   tmin, tmax);
-        // lanes without a left neighbour at distance d add kNegInf instead of being predicated:
-        // every value that travels is a real cell score here (>= kNeg - |small|), so the sum stays
-        // above INT_MIN and below every real score
+        const int edge = go + (r + 1) * ge;
 #pragma unroll
-        for (int d = 1; d < G; d <<= 1)
+        for (int k = 0; k < C; ++k)
         {
-          const int pen = (gl >= d) ? d * C * ge : kNegInf;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-            agg[a] = imax(agg[a], __shfl_up_sync(kFull, agg[a], d) + pen);
-        }
-        {
-          const int pen = (gl > 0) ? ge : kNegInf;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-          {
-            carry[a] = (G > 1) ? __shfl_up_sync(kFull, agg[a], 1) : 0;
-            best[a] = imax(best[a], carry[a] + pen);   // ge <= 0: the carry peaks at cell 0
-          }
+          const int K = K0 + k;
+          const bool real = K < W;
+          const int t = r - B + K;
+          const bool inb = real && (t >= tmin) && (t <= tmax);
+          const int E = (K < B && r < B) ? edge : kOob;
+          const int Dk = (K >= W - 1) ? kNeg : Dd[k];
+          const int4 m4 = *reinterpret_cast<const int4 *>(lutb + win_byte(win[k >> 2], k & 3));
+          const int v0 = inb ? imax(Pp[k] + m4.x, Dk) : E;
+          const int v1 = inb ? imax(Pp[k] + m4.y, Dk) : E;
+          const int v2 = inb ? imax(Pp[k] + m4.z, Dk) : E;
+          const int v3 = inb ? imax(Pp[k] + m4.w, Dk) : E;
+          best[0] = real ? imax(best[0], v0) : best[0];
+          best[1] = real ? imax(best[1], v1) : best[1];
+          best[2] = real ? imax(best[2], v2) : best[2];
+          best[3] = real ? imax(best[3], v3) : best[3];
         }
       }
       else
       {
-        int nobest[4] = {0, 0, 0, 0};
-        band_pass<C, G, WS, true, 4, false, false, false, false>(Sp, Gp, SpN, GpN, win, lutb, 0, go, ge, sin4,
-                                                   gin, agg, nobest, 0, idx_dummy, gl, W, B, r,
-                                                   tmin, tmax);
-        // (aggregate, transfer) scan: an out-of-bounds cell anywhere in a lane blocks the carry
-        int T = (lane_ok && nreal == C) ? C * ge : kNegInf;
-#pragma unroll
-        for (int d = 1; d < G; d <<= 1)
-        {
-          const int Tu = __shfl_up_sync(kFull, T, d);
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-          {
-            const int up = __shfl_up_sync(kFull, agg[a], d);
-            if (gl >= d)
-              agg[a] = imax(agg[a], imax(up, kNegInf) + T);
-          }
-          if (gl >= d)
-            T = imax(T + Tu, kNegInf);
-        }
-        int gin2[4];
-#pragma unroll
+        // positive gap penalties: the full row of every candidate, without committing it
+        const bool open = (r - B + K0 >= tmin) && (r - B + K0 + C - 1 <= tmax) && (nreal == C);
+        const RowDbg nodbg = {nullptr, nullptr, 0, false};
+#pragma unroll 1
         for (int a = 0; a < 4; ++a)
         {
-          carry[a] = (G > 1) ? __shfl_up_sync(kFull, agg[a], 1) : 0;
-          gin2[a] = (gl == 0) ? (kNeg - ge) : carry[a];
+          int nob = 0, noi = 0, noh = 0;
+          const int agg = exact_pass<C, false, false>(Pp, Dd, win, lutb, a, go, ge, (gl == 0) ? kNeg : kNegInf, gl, W,
+                                                      B, r, tmin, tmax, nob, 0, noi, noh, nodbg);
+          const int hin = carry_scan_exact<C, G>(agg, open, ge, gl);
+          int b = kNeg;
+          exact_pass<C, true, false>(Pp, Dd, win, lutb, a, go, ge, hin, gl, W, B, r, tmin, tmax, b, 0, noi, noh,
+                                     nodbg);
+          best[a] = b;
         }
-        int agg2[4];
-        band_pass<C, G, WS, true, 4, false, true, false, true>(Sp, Gp, SpN, GpN, win, lutb, 0, go, ge, sin4,
-                                                  gin2, agg2, best, 0, idx_dummy, gl, W, B, r,
-                                                  tmin, tmax);
       }
       // row best over the instance's G lanes
 #pragma unroll
@@ -692,7 +700,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       curr = (int) sums[besta];
     }
 
-    if (dbg_any && F->dbg_best != nullptr)
+    if (F->dbg_best != nullptr)
     {
       if (valid && gl == 0)
       {
@@ -709,66 +717,128 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     if (!alldead)
     {
       const int bestb = sel4(besta, best[0], best[1], best[2], best[3]);
-      int cs[1] = {sel4(besta, sin4[0], sin4[1], sin4[2], sin4[3])};
-      int cg[1] = {(gl == 0) ? (kNeg - ge) : sel4(besta, carry[0], carry[1], carry[2], carry[3])};
-      int gout1[1], nob[1] = {0};
       int idx = kBig;
-      if (dbg_path != nullptr && valid)
+      if (fast)
       {
-        // Gp holds the deletion term D of every cell until the commit overwrites it
+        // local pass: S, the chain y/H and the cell value with no carry from the lane to the left
+        uint32_t wa[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i)
+          wa[i] = win[i] | (0x04040404u * (unsigned) besta);   // LUT offset of m[code][besta]
+        unsigned hits[HW];
+#pragma unroll
+        for (int i = 0; i < HW; ++i)
+          hits[i] = 0;
+        int hprev = (gl == 0) ? kNeg : kNegInf;
+        int h0 = 0;
 #pragma unroll
         for (int k = 0; k < C; ++k)
-          if (gl * C + k < W)
-            F->dbg_del[(size_t) inst * W + gl * C + k] = Gp[k];
+        {
+          const int m = *reinterpret_cast<const int *>(lutb + win_byte(wa[k >> 2], k & 3));
+          const int S = Pp[k] + m;
+          const int y = imax(S + goe, Dd[k] + ge);
+          const int pn = imax3(S, Dd[k], hprev);
+          const int hn = imax(hprev + ge, y);
+          Pp[k] = pn;
+          if (k == 0)
+            h0 = hn;
+          else
+            Dd[k - 1] = hn;
+          hprev = hn;
+          if (G == 1 && pn == bestb && k <= kR)
+            hits[k >> 5] |= 1u << (k & 31);
+        }
+        if (G > 1)
+        {
+          // carry: max-plus prefix scan of the lane aggregates, decay C * ge per lane. Lanes without
+          // a left neighbour at distance d add kNegInf instead of being predicated: every value
+          // that travels is a real cell score, so the sum stays above INT_MIN and below every score
+          int agg = hprev;
+#pragma unroll
+          for (int d = 1; d < G; d <<= 1)
+          {
+            const int pen = (gl >= d) ? d * C * ge : kNegInf;
+            agg = imax(agg, __shfl_up_sync(kFull, agg, d) + pen);
+          }
+          int c = __shfl_up_sync(kFull, agg, 1);
+          c = (gl > 0) ? c : kNegInf;
+          // fold the carry in: cell k sees carry + k * ge, its H carry + (k+1) * ge
+#pragma unroll
+          for (int k = 0; k < C; ++k)
+          {
+            const int pn = imax(Pp[k], c);
+            Pp[k] = pn;
+            if (pn == bestb && (k <= kR || !is_last))
+              hits[k >> 5] |= 1u << (k & 31);
+            c += ge;
+            if (k == 0)
+              h0 = imax(h0, c);
+            else
+              Dd[k - 1] = imax(Dd[k - 1], c);
+          }
+          Dd[C - 1] = __shfl_down_sync(kFull, h0, 1);
+        }
+        // cells right of the band: offset == bandwidth has no deletion, padding cells stay inert
+#pragma unroll
+        for (int k = kR; k < C; ++k)
+        {
+          if (G == 1)
+          {
+            Dd[k] = (k == kR) ? kNeg : kNegInf;
+            if (k > kR)
+              Pp[k] = kNegInf;
+          }
+          else
+          {
+            Dd[k] = is_last ? ((k == kR) ? kNeg : kNegInf) : Dd[k];
+            if (k > kR)
+              Pp[k] = is_last ? kNegInf : Pp[k];
+          }
+        }
+        int md = kNeg;
+#pragma unroll
+        for (int k = 0; k + 1 < C; k += 2)
+          md = imax3(md, Dd[k], Dd[k + 1]);
+        if (C & 1)
+          md = imax(md, Dd[C - 1]);
+        maxD = md;
+#pragma unroll
+        for (int i = HW - 1; i >= 0; --i)
+          if (hits[i])
+            idx = 32 * i + __ffs((int) hits[i]) - 1;
       }
-      if (fast)
-        band_pass<C, G, WS, false, 1, true, false, true, false>(Sp, Gp, SpN, GpN, win, lutb, besta, go, ge, cs,
-                                                   cg, gout1, nob, bestb, idx, gl, W, B, r, tmin,
-                                                   tmax);
       else
-        band_pass<C, G, WS, true, 1, true, false, true, false>(Sp, Gp, SpN, GpN, win, lutb, besta, go, ge, cs,
-                                                  cg, gout1, nob, bestb, idx, gl, W, B, r, tmin,
-                                                  tmax);
-      int kidx = (idx < kBig) ? gl * C + idx : kBig;
+      {
+        const bool open = (r - B + K0 >= tmin) && (r - B + K0 + C - 1 <= tmax) && (nreal == C);
+        const RowDbg nodbg = {nullptr, nullptr, 0, false};
+        const RowDbg dbg = {dbg_rows ? dbg_rows + (size_t) r * n_ext * W * 2 : nullptr,
+                            dbg_path ? dbg_path + (size_t) r * n_ext * W : nullptr, inst, valid};
+        int nob = 0, noi = 0, h0 = 0;
+        const int agg = exact_pass<C, false, false>(Pp, Dd, win, lutb, besta, go, ge, (gl == 0) ? kNeg : kNegInf, gl,
+                                                    W, B, r, tmin, tmax, nob, 0, noi, h0, nodbg);
+        const int hin = carry_scan_exact<C, G>(agg, open, ge, gl);
+        exact_pass<C, true, true>(Pp, Dd, win, lutb, besta, go, ge, hin, gl, W, B, r, tmin, tmax, nob, bestb, idx,
+                                  h0, dbg);
+        Dd[C - 1] = (G > 1) ? __shfl_down_sync(kFull, h0, 1) : kNeg;
+        int md = kNeg;
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+        {
+          const int K = K0 + k;
+          Dd[k] = (K < W - 1) ? Dd[k] : (K == W - 1) ? kNeg : kNegInf;
+          md = imax(md, Dd[k]);
+        }
+        maxD = md;
+      }
+      int kidx = (idx < kBig) ? K0 + idx : kBig;
       kidx = group_min<G>(kidx, gl, lane);
       if (bestb > high)   // record setter, ram_extend.c:1140-1150
       {
         high = bestb;
         pos = r - B + kidx;
       }
-      if (dbg_rows != nullptr && valid)
-      {
-#pragma unroll
-        for (int k = 0; k < C; ++k)
-        {
-          const int K = gl * C + k;
-          if (K < W)
-          {
-            int *o = dbg_rows + (((size_t) r * n_ext + inst) * W + K) * 2;
-            o[0] = Sp[k];
-            o[1] = Gp[k];
-          }
-        }
-      }
-      if (dbg_path != nullptr && valid)
-      {
-        // sub == cell -> substitution, else del == cell -> deletion, else insertion
-        // (bnw_extend.c:1036-1041; each thread reads back the D it stored above)
-#pragma unroll
-        for (int k = 0; k < C; ++k)
-        {
-          const int K = gl * C + k;
-          if (K < W)
-          {
-            const int cell = imax(Sp[k], Gp[k]);
-            const int del = F->dbg_del[(size_t) inst * W + K];
-            dbg_path[((size_t) r * n_ext + inst) * W + K] =
-              (unsigned char) ((Sp[k] == cell) ? 0 : (del == cell) ? 1 : 2);
-          }
-        }
-        if (gl == 0)
-          F->dbg_idx[(size_t) r * n_ext + inst] = kidx;
-      }
+      if (dbg_path != nullptr && valid && gl == 0)
+        F->dbg_idx[(size_t) r * n_ext + inst] = kidx;
     }
 
     // ---- improvement / stop rule (ram_extend.c:1194-1223) ------------------------------------
@@ -789,7 +859,9 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
 
     // ---- slide the base window by one band position ------------------------------------------
     {
-      uint32_t in = (uint32_t) (newc << 4);
+      uint32_t in = (nib_lo << 4) & 0xf0u;
+      nib_lo = __funnelshift_r(nib_lo, nib_hi, 4);
+      nib_hi >>= 4;
       if (G > 1)
       {
         const uint32_t nb = __shfl_down_sync(kFull, win[0] & 0xffu, 1);

@@ -625,12 +625,20 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
                 RAMCU_MAX_BANDWIDTH);
   if (pr->L > (1 << 24))
     return fail(RAMCU_ERR_UNSUPPORTED, "L %d larger than %d", pr->L, 1 << 24);
-  for (int a = 0; a < 4; ++a)
-    for (int b = 0; b < RAMCU_NCODES; ++b)
-      if (abs(sc->matrix[a][b]) > 100000)
-        return fail(RAMCU_ERR_UNSUPPORTED, "matrix value %d too large", sc->matrix[a][b]);
-  if (abs(sc->gapopen) > 100000 || abs(sc->gapextn) > 100000)
-    return fail(RAMCU_ERR_UNSUPPORTED, "gap penalties too large");
+  {
+    // Every value the reference computes stays above its own -1000000000 floor (bnw_extend.c:802-804) when
+    // the out-of-bounds sentinel -987654321 cannot drift that far: a path adds at most `worst` per step and
+    // has at most L + 2B + 2 steps. The kernel relies on that (it never applies the floor); the reference's
+    // matrices and any sensible -gapopen/-gapext/-match/-mismatch are three orders of magnitude inside it.
+    long long worst = (long long) llabs((long long) sc->gapopen) + llabs((long long) sc->gapextn);
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < RAMCU_NCODES; ++b)
+        worst = std::max(worst, (long long) llabs((long long) sc->matrix[a][b]));
+    if (worst * ((long long) pr->L + 2LL * pr->bandwidth + 3) > 12000000LL)
+      return fail(RAMCU_ERR_UNSUPPORTED,
+                  "scores of magnitude %lld over L + band = %lld steps can cross the reference's -1000000000 "
+                  "floor (limit: magnitude x steps <= 12000000)", worst, (long long) pr->L + 2LL * pr->bandwidth + 3);
+  }
   CK(cudaSetDevice(c->device));
 
   ramcu_job *j = new ramcu_job();

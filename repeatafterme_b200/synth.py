@@ -284,7 +284,7 @@ def family_twobit_windows(fam: Family):
 
 def config5_parity_sample(specs=None, seed: int = 11):
     """Seeded, stratified sample of the config-5 family mix used to pin parity at FULL size against
-    the reference (tests/golden/flat_config5_sample.npz): for every bandwidth one family from each
+    the reference (tests/golden/full_config5_sample.npz): for every bandwidth one family from each
     of four size strata (N < 300, < 1000, < 3500, >= 3500; families above 3e10 cell updates are left
     out to bound the reference's CPU time) plus, for bandwidth 40 and 100, the cheapest family with
     N >= 5000 that is not picked already. Returns indices into `specs`."""

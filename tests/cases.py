@@ -285,12 +285,12 @@ def _wide_keys():
     return [(k, _cu(v["n"], v["params"]["bandwidth"], v["flank"])) for k, v in WIDE_CASES.items()]
 
 
-FULL_CASES = {"config4_full": _config4_keys, "config5_sample": _config5_keys, "wide_bands": _wide_keys}
+FULL_CASES = {"config4": _config4_keys, "config5_sample": _config5_keys, "wide_bands": _wide_keys}
 
 
 def full_case_family(group, key):
     """the synth.Family (with .params) of one full-size case"""
-    if group == "config4_full":
+    if group == "config4":
         fam = synth.make_family(4, 10000, 5000, 0.15)      # exactly bench.py's rank-0 family
         fam.params = dict(CONFIG4)
         return fam

@@ -98,6 +98,23 @@ static inline int __reduce_max_sync(unsigned, int v)
   pthread_barrier_wait(&emul_warp->bar);
   return m;
 }
+static inline int __reduce_min_sync(unsigned, int v)
+{
+  const int lane = threadIdx.x & 31;
+  emul_warp->buf[lane] = v;
+  pthread_barrier_wait(&emul_warp->bar);
+  int m = (int) emul_warp->buf[0];
+  for (int i = 1; i < 32; ++i) m = ((int) emul_warp->buf[i] < m) ? (int) emul_warp->buf[i] : m;
+  pthread_barrier_wait(&emul_warp->bar);
+  return m;
+}
+static inline unsigned __brev(unsigned x)
+{
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+  return __builtin_bswap32(x);
+}
 static inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __sync_fetch_and_add(p, v); }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __sync_fetch_and_or(p, v); }

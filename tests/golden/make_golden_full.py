@@ -1,13 +1,13 @@
 """Reference outputs at the BENCHMARKED sizes (run in the build container, where /root/reference
 and oracle/_ref exist):  python tests/golden/make_golden_full.py [config4] [config5] [wide]
 
-  flat_config4_full.npz     BASELINE configs[3] exactly as bench.py generates it
+  full_config4.npz          BASELINE configs[3] exactly as bench.py generates it
                             (synth.make_family(4, 10000, 5000, 0.15), bandwidth 40, 14p43g): the
                             outputs of the reference's extend_alignment() object code for both
                             directions (~800 s of one core per run)
-  flat_config5_sample.npz   synth.config5_parity_sample(): 22 families of the configs[4] mix at FULL
+  full_config5_sample.npz   synth.config5_parity_sample(): 22 families of the configs[4] mix at FULL
                             size (every bandwidth, four size strata, six families with N >= 5000)
-  flat_wide_bands.npz       bandwidth 500 (util/davidExtendConsRAM.pl:248), 511 and 100 with a
+  full_wide_bands.npz       bandwidth 500 (util/davidExtendConsRAM.pl:248), 511 and 100 with a
                             family that spans more than 40 CTAs
 
 Inputs are NOT stored: they are regenerated from the seeds; the fixture holds the sha256 of the
@@ -74,7 +74,7 @@ def main():
             m = meta.setdefault(k, dict(n=o["n"], params=o["params"], seq_sha=o["seq_sha"],
                                         cores_sha=o["cores_sha"]))
             m[f"bp{d}"], m[f"rows{d}"], m[f"ref_seconds{d}"] = o["bp"], o["rows"], round(o["seconds"], 1)
-        np.savez_compressed(os.path.join(HERE, f"flat_{g}.npz"), meta=json.dumps(meta), **arrays)
+        np.savez_compressed(os.path.join(HERE, f"full_{g}.npz"), meta=json.dumps(meta), **arrays)
         print("wrote", g, len(meta), "families")
 
 

@@ -78,3 +78,27 @@ def load_cli(name):
     want = {f: open(os.path.join(d, f)).read() for f in ("stdout.txt", "out.tsv", "out.fa", "cons.fa")}
     return dict(names=meta["names"], seqs=seqs, bed=[tuple(b) for b in meta["bed"]], flags=meta["flags"],
                 want=want)
+
+
+def load_full(group):
+    """reference outputs at the benchmarked sizes (tests/golden/make_golden_full.py): inputs are
+    regenerated from seeds by tests.cases.full_case_family and checked against the stored sha256.
+    -> {key: dict(n, params, seq_sha, cores_sha, want={1: {...}, 0: {...}})}"""
+    z = np.load(os.path.join(GOLDEN, f"full_{group}.npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    out = {}
+    for k, m in meta.items():
+        want = {}
+        for d in (1, 0):
+            want[d] = dict(extended_bp=int(m[f"bp{d}"]), rows_processed=int(m[f"rows{d}"]),
+                           master=z[f"{k}_master{d}"], ext_len=z[f"{k}_ext_len{d}"],
+                           score_add=z[f"{k}_score_add{d}"])
+        out[k] = dict(n=m["n"], params=m["params"], seq_sha=m["seq_sha"], cores_sha=m["cores_sha"], want=want)
+    return out
+
+
+def check_full_inputs(fam, case):
+    """the regenerated inputs are the ones the reference saw"""
+    import hashlib
+    assert hashlib.sha256(np.ascontiguousarray(fam.sequence).tobytes()).hexdigest() == case["seq_sha"], "generator drifted (sequence)"
+    assert hashlib.sha256(np.ascontiguousarray(fam.cores).tobytes()).hexdigest() == case["cores_sha"], "generator drifted (cores)"

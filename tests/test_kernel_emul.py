@@ -138,3 +138,37 @@ def test_emul_twobit_decode(emul, seed, n, flank, kw):
     seq = np.asarray(fam.sequence)
     known = seq <= 3
     assert np.array_equal(want[known], seq[known])   # and that is the reference loader's byte per base
+
+
+@pytest.mark.parametrize("cfg,B,matrix", [
+    ((29, 1, 29), 14, "20p43g"), ((15, 2, 29), 14, "20p43g"), ((10, 3, 29), 14, "25p43g"), ((8, 4, 29), 14, "14p43g"),
+    ((5, 6, 29), 14, "18p43g"), ((4, 8, 29), 14, "20p43g"), ((27, 3, 81), 40, "14p43g"), ((41, 2, 81), 40, "14p43g"),
+    ((17, 5, 81), 40, "18p43g"),
+])
+def test_emul_fast_rows(emul, oracle, cfg, B, matrix):
+    """long flanks inside generous sequence bounds: nearly every row takes the unpredicated path
+    (chain-free sweep, local commit + carry fold-in), then the flank ends and the exact path takes
+    over; two CTAs, N bases, one-sided cores"""
+    fam = synth.make_family(77 + cfg[0], 11, 260, 0.15, pad=3 * B, one_sided_frac=0.2, n_frac=0.01)
+    osc = oracle.scoring(matrix)
+    p = make_params(bandwidth=B, minimprovement=27, L=1000, when_to_stop=30)
+    for d in (1, 0):
+        want = oracle.extend(d, fam.cores, fam.sequence, osc, p, trace=True)
+        assert want["rows_processed"] > 150
+        got = emul.extend(cfg, d, fam.cores, fam.sequence, osc.to_product(), p, threads=64)
+        support.compare_extend(want, got, f"cfg={cfg} dir={d}")
+
+
+@pytest.mark.parametrize("cfg,gaps", [((8, 4, 29), (3, -4)), ((10, 3, 29), (-6, 1)), ((29, 1, 29), (2, 2)),
+                                      ((16, 4, 0), (4, -2)), ((15, 2, 29), (0, 0))])
+def test_emul_positive_gap_penalties(emul, oracle, cfg, gaps):
+    """-gapopen / -gapext accept any integer (ram_extend.c:292-293): with a positive penalty the
+    insertion term can exceed the cell left of it, so the chain-free sweep does not apply"""
+    fam = synth.make_family(91, 9, 120, 0.2, pad=40, one_sided_frac=0.2)
+    osc = oracle.scoring("20p43g")
+    osc.gapopen, osc.gapextn = gaps
+    p = make_params(bandwidth=14, minimprovement=27, L=90, when_to_stop=30)
+    for d in (1, 0):
+        want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+        got = emul.extend(cfg, d, fam.cores, fam.sequence, osc.to_product(), p, threads=64)
+        support.compare_extend(want, got, f"cfg={cfg} gaps={gaps} dir={d}")
