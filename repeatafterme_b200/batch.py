@@ -75,9 +75,19 @@ def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
         # Without a between-passes step (the overlap avoidance of ram_extend.c:445-499 belongs to the
         # caller) the left passes do not depend on the right ones: all 2 x len(fams) column loops go
         # into one batch and share the SMs. With one, right batch -> hook -> left batch.
-        rounds = [(1, 0)] if between_passes is None else [(1,), (0,)]
-        for dirs in rounds:
-            jobs = [(i, d, rc.job_create(libs[i], d, f.cores, scs[i], prs[i])) for d in dirs for i, f in enumerate(fams)]
+        if between_passes is None:
+            # the two passes of a family are created as a linked pair (ramcu_job_create_pair): where both
+            # row states fit the register file, every thread carries a band of both and the passes take turns
+            jobs = []
+            for i, f in enumerate(fams):
+                r, l = rc.job_create_pair(libs[i], f.cores, scs[i], prs[i])
+                jobs += [(i, 1, r), (i, 0, l)]
+            rounds = [jobs]
+        else:
+            rounds = [(1,), (0,)]
+        for rnd in rounds:
+            jobs = rnd if isinstance(rnd, list) else [(i, d, rc.job_create(libs[i], d, f.cores, scs[i], prs[i]))
+                                                      for d in rnd for i, f in enumerate(fams)]
             if len(jobs) == 1:
                 rc.job_run(jobs[0][2])
             else:
@@ -89,7 +99,7 @@ def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
                 else:
                     results[i].left = out
                 rc.job_free(j)
-            if dirs == (1,):
+            if rnd == (1,):
                 for i, f in enumerate(fams):
                     between_passes(f, results[i].right)
     finally:

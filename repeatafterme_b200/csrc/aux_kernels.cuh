@@ -165,7 +165,7 @@ twobit_windows_kernel(const uint8_t *__restrict__ blob, const unsigned long long
                       const WindowDev *__restrict__ win, const int n_win,
                       const unsigned long long total, uint32_t *__restrict__ lib2,
                       const unsigned long long n_chunks, unsigned long long *__restrict__ slow_list,
-                      unsigned int *__restrict__ slow_count)
+                      unsigned int *__restrict__ slow_count, const unsigned int slow_cap)
 {
   const unsigned long long n_groups = (n_chunks + 3) / 4;
   for (unsigned long long g = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,7 +220,17 @@ twobit_windows_kernel(const uint8_t *__restrict__ blob, const unsigned long long
       dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
     }
     else
-      slow_list[atomicAdd(slow_count, 1u)] = g;
+    {
+      // the list holds one group per window boundary plus the tail; callers may also hand in windows
+      // whose sources sit in the last bytes of the blob (no whole 16-byte loads): past the list's
+      // capacity the group is decoded right here
+      const unsigned int idx = atomicAdd(slow_count, 1u);
+      if (idx < slow_cap)
+        slow_list[idx] = g;
+      else
+        for (unsigned long long ch = g * 4; ch < g * 4 + 4 && ch < n_chunks; ++ch)
+          twobit_chunk_slow(blob, blob_bytes, win, n_win, total, lib2, ch);
+    }
   }
 }
 
@@ -230,9 +240,9 @@ twobit_boundary_kernel(const uint8_t *__restrict__ blob, const unsigned long lon
                        const WindowDev *__restrict__ win, const int n_win,
                        const unsigned long long total, uint32_t *__restrict__ lib2,
                        const unsigned long long n_chunks, const unsigned long long *__restrict__ slow_list,
-                       const unsigned int *__restrict__ slow_count)
+                       const unsigned int *__restrict__ slow_count, const unsigned int slow_cap)
 {
-  const unsigned long long n = 4ull * *slow_count;
+  const unsigned long long n = 4ull * min(*slow_count, slow_cap);
   for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long) gridDim.x * blockDim.x)
   {
@@ -263,6 +273,24 @@ nmask_ranges_kernel(const unsigned long long *__restrict__ start,
     if (w == w1)
       m &= 0xffffffffu >> (31 - ((e - 1) & 31));
     atomicOr(libn + w, m);
+  }
+}
+
+// one range handed over by value (the positions past the library inside its last mask word)
+__global__ void nmask_one_range_kernel(const unsigned long long s, const unsigned long long len, uint32_t *__restrict__ libn)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0 && len > 0)
+  {
+    const unsigned long long e = s + len;
+    for (unsigned long long w = s >> 5; w <= ((e - 1) >> 5); ++w)
+    {
+      uint32_t m = 0xffffffffu;
+      if (w == (s >> 5))
+        m &= 0xffffffffu << (s & 31);
+      if (w == ((e - 1) >> 5))
+        m &= 0xffffffffu >> (31 - ((e - 1) & 31));
+      atomicOr(libn + w, m);
+    }
   }
 }
 

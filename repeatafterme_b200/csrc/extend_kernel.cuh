@@ -70,21 +70,20 @@ struct FamDev
   int *thigh;             // out: trimmed_sequence_high_score      (per extendable instance)
   int *tpos;              // out: trimmed_sequence_high_score_pos
   int *result;            // out: [0] max_row [1] rows_processed [2] stop_row [3] max_ext
-  unsigned long long *slots;    // column exchange area, zeroed before each launch:
-                                // [2][n_ctas][4] (tag << 32 | sum) slots, or, for more than
-                                // kSlotMaxCtas CTAs, [L][4] (count << 48 | sum) accumulators
+  unsigned long long *slots;    // column exchange area of a multi-CTA family, zeroed before each
+                                // launch: [L][4] (count << 48 | sum) accumulators
   const unsigned char *forced;  // debug: forced consensus per row (or NULL)
   int *dbg_rows;          // debug: [rows][n_ext][W][2]
   int *dbg_best;          // debug: [rows][n_ext][4]
   int *dbg_sums;          // debug: [rows][4]
   unsigned char *dbg_path;   // -outmat: [rows][n_ext][W] state of the best path into each cell of the
                              // committed row: 0 substitution, 1 deletion, 2 insertion (bnw_extend.c:1027-1044)
-  int *dbg_del;           // -outmat scratch: [n_ext][W] deletion term of the row being committed
   int *dbg_idx;           // -outmat: [rows][n_ext] band index of the row's first best cell
   long long *dbg_wait;    // diagnostics: per CTA [0] cycles spent in the grid exchange [1] total cycles
   int n_ext, n_ctas, cta0, B;
   int W, go, ge, cap;
-  int minimp, L, stop, pad;
+  int minimp, L, stop;
+  int mate;               // index of the family's other pass in the same launch (two-pass CTAs), or -1
   int m[8][4];            // m[code][cand]; code 4 = N, 5 = out of bounds (value unused)
 };
 
@@ -344,125 +343,103 @@ __device__ __forceinline__ int carry_scan_exact(int agg, const bool open, const 
   return (gl == 0) ? kNeg : cin;   // offset == -bandwidth: no insertion (bnw_extend.c:972)
 }
 
-// Grid-level exchange of the four per-candidate column sums between the CTAs of a family.
-// Every CTA publishes its four sums as (tag << 32 | sum) 64-bit words in its own 32-byte slot
-// (plain stores: no atomics, no serialisation point in L2); warp 0 of every CTA then gathers all
-// slots, kGatherU independent 32-byte loads per lane in flight, and re-reads only the slots whose
-// tag (column + 1) has not arrived yet. The tag travels in the same word as the data, so no fence
-// is needed and one L2 round trip suffices once the last CTA has published. Slots are double
-// buffered by column parity: a CTA overwrites a slot two columns later, after everyone read it.
-constexpr int kGatherU = 2;   // 64 slots per round covers the <= kSlotMaxCtas CTAs of this path
+// Column exchange between the CTAs of a family: column r owns four 64-bit accumulators (zeroed before
+// the launch) and every CTA adds (1 << 48 | partial) with one RED per candidate, so the arrival count
+// travels in the same word as the data: a reader that sees count == n_ctas has the complete sum in
+// the low 32 bits (mod 2^32, exactly the reference's int arithmetic). No fence, no reset.
+constexpr int kRedStride = 1;      // 64-bit words between the accumulators of one column
 
-__device__ __forceinline__ void ld_slot(const unsigned long long *p, unsigned long long (&w)[4])
+// ---------------------------------------------------------------------------------------------
+// per-column handshake of one pass: CTA-level sum of the warps' contributions, grid-level sum of
+// the CTAs' contributions, delivery of the column sums to every warp -- without a CTA barrier
+// ---------------------------------------------------------------------------------------------
+// Column c uses slot c & 1. Contribution: lane 0 of every warp adds its four partial sums to
+// acc[slot] (shared-memory atomics) and then counts itself in cnt[slot]; the warp that counts last
+// owns the CTA's sums: it clears the slot and either publishes them (family on one CTA) or adds them
+// to the column's global accumulators (one RED per candidate, the arrival count in the upper bits).
+// Delivery: warp 0 polls the global accumulators and publishes the complete sums; every warp waits
+// for res_tag[slot] == c + 1 when it next needs the column, i.e. after it has done the other pass's
+// row in between. A slot is reused two columns later, which every warp of the CTA can only reach
+// after it has consumed this column.
+struct PassShared
+{
+  int acc[2][4];
+  int res[2][4];
+  int cnt[2];
+  int res_tag[2];
+};
+
+__device__ __forceinline__ int ld_volatile_shared(const int *p)
 {
 #ifdef RAMCU_EMUL
-  for (int i = 0; i < 4; ++i)
-    w[i] = emul_ld_relaxed_u64(p + i);
+  sched_yield();
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 #else
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
-               : "=l"(w[0]), "=l"(w[1]) : "l"(p) : "memory");
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
-               : "=l"(w[2]), "=l"(w[3]) : "l"(p + 2) : "memory");
+  return *reinterpret_cast<const volatile int *>(p);
+#endif
+}
+__device__ __forceinline__ void st_volatile_shared(int *p, int v)
+{
+#ifdef RAMCU_EMUL
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
+  *reinterpret_cast<volatile int *>(p) = v;
 #endif
 }
 
-__device__ __forceinline__ void grid_exchange(unsigned long long *slots, const int n_ctas,
-                                              const int cta_in_fam, const int par,
-                                              const unsigned tag, unsigned (&sums)[4],
-                                              const int lane)
+// Waiting is bounded: the exchange relies on every CTA of a family being resident (launch layout,
+// ramcu.cu). If another process or kernel holds SMs of the device that can fail; the kernel then
+// traps (tens of seconds) and the host reports an error instead of hanging for ever.
+constexpr unsigned kMaxGlobalSpins = 1u << 27;
+constexpr unsigned kMaxSharedSpins = 1u << 30;
+__device__ __forceinline__ void spin_timeout()
 {
-  unsigned long long *base = slots + (size_t) par * n_ctas * 4;
-  if (lane < 4)
-  {
-    const unsigned mine = (unsigned) sel4(lane, (int) sums[0], (int) sums[1], (int) sums[2], (int) sums[3]);
-    st_relaxed_u64(base + (size_t) cta_in_fam * 4 + lane, ((unsigned long long) tag << 32) | mine);
-  }
-  unsigned acc[4] = {0, 0, 0, 0};
-  for (int b0 = 0; b0 < n_ctas; b0 += 32 * kGatherU)
-  {
-    unsigned long long w[kGatherU][4];
-    bool done[kGatherU];
-#pragma unroll
-    for (int u = 0; u < kGatherU; ++u)
-      done[u] = (b0 + u * 32 + lane) >= n_ctas;
-    bool all;
-    do
-    {
-#pragma unroll
-      for (int u = 0; u < kGatherU; ++u)
-        if (!done[u])
-          ld_slot(base + (size_t) (b0 + u * 32 + lane) * 4, w[u]);
-      all = true;
-#pragma unroll
-      for (int u = 0; u < kGatherU; ++u)
-        if (!done[u])
-        {
-          const bool ok = ((unsigned) (w[u][0] >> 32) == tag) && ((unsigned) (w[u][1] >> 32) == tag) &&
-                          ((unsigned) (w[u][2] >> 32) == tag) && ((unsigned) (w[u][3] >> 32) == tag);
-          if (ok)
-          {
-            done[u] = true;
-            acc[0] += (unsigned) w[u][0];
-            acc[1] += (unsigned) w[u][1];
-            acc[2] += (unsigned) w[u][2];
-            acc[3] += (unsigned) w[u][3];
-          }
-          else
-            all = false;
-        }
-    } while (!all);
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-    sums[a] = (unsigned) __reduce_add_sync(kFull, (int) acc[a]);
+#ifdef RAMCU_EMUL
+  abort();
+#else
+  __trap();
+#endif
 }
 
-// Large families (more than kSlotMaxCtas CTAs): the all-to-all slot gather above would make every
-// CTA read every slot; instead column r owns four 64-bit accumulators (zeroed before the launch)
-// and every CTA adds (1 << 48 | partial) with one RED per candidate, so the arrival count travels
-// in the same word as the data: a reader that sees count == n_ctas has the complete sum in the
-// low 32 bits (mod 2^32, exactly the reference's int arithmetic). No fence, no reset.
-constexpr int kSlotMaxCtas = 40;
-constexpr int kRedStride = 1;      // 64-bit words between the accumulators of one column
-
-__device__ __forceinline__ void grid_exchange_red(unsigned long long *acc_row, const int n_ctas,
-                                                  unsigned (&sums)[4], const int lane)
-{
-  unsigned lo = 0;
-  if (lane < 4)
-  {
-    const unsigned mine = (unsigned) sel4(lane, (int) sums[0], (int) sums[1], (int) sums[2], (int) sums[3]);
-    // the four accumulators of a column sit in four different 128-byte lines (four L2 slices
-    // serve the REDs and the polls in parallel)
-    unsigned long long *word = acc_row + lane * kRedStride;
-    atomicAdd(word, (1ull << 48) | (unsigned long long) mine);
-    unsigned long long v;
-    do
-    {
-      v = ld_relaxed_u64(word);
-    } while ((int) (v >> 48) != n_ctas);
-    lo = (unsigned) v;
-  }
-  sums[0] = __shfl_sync(kFull, lo, 0);
-  sums[1] = __shfl_sync(kFull, lo, 1);
-  sums[2] = __shfl_sync(kFull, lo, 2);
-  sums[3] = __shfl_sync(kFull, lo, 3);
-}
-
-// per-CTA shared state: score LUT, per-warp partial column sums, broadcast sums, logical CTA id
+// per-CTA shared state: score LUT, the handshake areas of the passes, logical CTA id
+template <int NP>
 struct SharedBlk
 {
   int4 lut[8];
-  int4 part[2][kMaxWarps];
-  int4 bcast[2];
+  PassShared ps[NP];
   int cta;
 };
 
-template <int C, int G, int WS, int MAXT>
+template <int P>
+struct PassTag
+{
+  static constexpr int value = P;
+};
+
+// registers of one pass (one direction of one family) in one thread
+template <int C>
+struct PassRegs
+{
+  int Pp[C], Dd[C];             // row state, see the header
+  uint32_t win[(C + 3) / 4];    // base window: byte k = LUT offset (code * 16) of cell k's base
+  uint32_t nib_lo, nib_hi;      // codes of the next band positions entering at the high end
+  int maxD;                     // max of Dd over the lane's real cells
+  int best[4];                  // row bests of the pending column (instance-wide)
+  int high, pos, thigh, tpos;   // ram_extend.c:900-914
+  int max_row, max_ext, stop_row;
+  long long start;              // instance geometry (InstDev)
+  int sgn, comp, tmin, tmax;
+  int r_fast_lo, r_fast_hi, r_dead;
+  int inst;
+  bool valid, active;
+};
+
+template <int C, int G, int WS, int MAXT, int NP>
 __global__ void __launch_bounds__(MAXT, 1)
 extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, int *ticket)
 {
   static_assert(G >= 1 && G <= 32, "1..32 lanes per instance");
+  static_assert(NP == 1 || NP == 2, "one pass, or the right and the left pass of a family");
   constexpr int IPW = 32 / G;   // instances per warp (lanes IPW*G..31 are spare when 32 % G != 0)
   static_assert(WS == 0 || ((G - 1) * C < WS && WS <= G * C), "band does not tile into G x C");
   constexpr int CW = (C + 3) / 4;
@@ -470,25 +447,23 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   // static band: index of the last real cell inside the last lane
   constexpr int kR = WS ? WS - 1 - (G - 1) * C : C - 1;
 
-  RAMCU_SHARED_STRUCT(SharedBlk, sh);
-  int4 (&s_lut)[8] = sh.lut;
-  int4 (&s_part)[2][kMaxWarps] = sh.part;
-  int4 (&s_bcast)[2] = sh.bcast;
-  int &s_cta = sh.cta;
+  RAMCU_SHARED_STRUCT(SharedBlk<NP>, sh);
 
   // logical CTA id in start order: the CTAs of a multi-CTA family are co-resident or ahead of
   // every CTA that could wait for them.
   if (threadIdx.x == 0)
-    s_cta = atomicAdd(ticket, 1);
+    sh.cta = atomicAdd(ticket, 1);
+  for (int i = threadIdx.x; i < NP * (int) (sizeof(PassShared) / sizeof(int)); i += blockDim.x)
+    reinterpret_cast<int *>(sh.ps)[i] = 0;
   __syncthreads();
-  const int cta = s_cta;
-  const FamDev *__restrict__ F = fams + cta_fam[cta];
-  const int cta_in_fam = cta - F->cta0;
+  const int cta = sh.cta;
+  const FamDev *__restrict__ F0 = fams + cta_fam[cta];
+  const int cta_in_fam = cta - F0->cta0;
   if (threadIdx.x < 8)
-    s_lut[threadIdx.x] = make_int4(F->m[threadIdx.x][0], F->m[threadIdx.x][1],
-                                   F->m[threadIdx.x][2], F->m[threadIdx.x][3]);
+    sh.lut[threadIdx.x] = make_int4(F0->m[threadIdx.x][0], F0->m[threadIdx.x][1],
+                                    F0->m[threadIdx.x][2], F0->m[threadIdx.x][3]);
   __syncthreads();
-  const char *lutb = reinterpret_cast<const char *>(s_lut);
+  const char *lutb = reinterpret_cast<const char *>(sh.lut);
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -496,78 +471,101 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   const int gl = lane % G;
   const int gw = lane / G;
   const bool is_last = (gl == G - 1);
+  const int K0 = gl * C;
 
-  const int B = F->B, W = WS ? WS : F->W;
-  const int go = F->go, ge = F->ge, goe = go + ge, cap = F->cap, minimp = F->minimp;
-  const int L = F->L, stop = F->stop, n_ext = F->n_ext, n_ctas = F->n_ctas;
+  // scalar parameters: the passes of a launch unit are the two directions of one family
+  const int B = F0->B, W = WS ? WS : F0->W;
+  const int go = F0->go, ge = F0->ge, goe = go + ge, cap = F0->cap, minimp = F0->minimp;
+  const int L = F0->L, stop = F0->stop, n_ctas = F0->n_ctas;
   // non-positive gap penalties: the insertion term of a cell never exceeds the cell left of it, so
   // the row best needs no insertion chain (sweep) and a carry can only raise a prefix of a lane
   const bool gaps_ok = (go <= 0) && (ge <= 0);
-  const unsigned char *forced = F->forced;
-  int *dbg_rows = F->dbg_rows;
-  unsigned char *dbg_path = F->dbg_path;
-  const bool dbg_on = (dbg_rows != nullptr) || (dbg_path != nullptr);
+  const int nreal = min(max(W - K0, 0), C);   // real (in-band) cells of this lane
 
-  // balanced partition of the family's instances over its CTAs (n_ctas <= n_ext)
-  const int first = (int) ((long long) cta_in_fam * n_ext / n_ctas);
-  const int next = (int) ((long long) (cta_in_fam + 1) * n_ext / n_ctas);
-  const int grp = warp * IPW + gw;
-  const bool valid = (gw < IPW) && (grp < next - first);
-  const int inst = valid ? first + grp : next - 1;   // padding lanes shadow the last instance
-  const InstDev I = F->inst[inst];
-  const uint32_t *lib2 = F->lib2, *libn = F->libn;
-  const int tmin = I.tmin, tmax = I.tmax;
-  const int K0 = gl * C;
+  const FamDev *Fp[NP];
+  PassRegs<C> ps[NP];
+  bool dbg_on[NP], use_fast[NP];
 
-  // row state (see the header): boundary row S = G = (o == 0 ? 0 : |o| * ge + go), ram_extend.c:909-946
-  int Pp[C], Dd[C];
-  uint32_t win[CW];
+  // ---- set-up of every pass: instance, boundary row, first base window ------------------------
 #pragma unroll
-  for (int i = 0; i < CW; ++i)
-    win[i] = 0;
-  int maxD = kNeg;
-#pragma unroll
-  for (int k = 0; k < C; ++k)
+  for (int p = 0; p < NP; ++p)
   {
-    const int K = K0 + k;
-    const int o = K - B;
-    const int v = (o == 0) ? 0 : abs(o) * ge + go;
-    const int v1 = (o + 1 == 0) ? 0 : abs(o + 1) * ge + go;
-    Pp[k] = (K < W) ? v : kNegInf;
-    Dd[k] = (K < W - 1) ? imax(v1 + goe, v1 + ge) : (K == W - 1) ? kNeg : kNegInf;
-    maxD = imax(maxD, Dd[k]);
-    const int code = fetch_code(lib2, libn, I.start, I.sgn, I.comp, tmin, tmax, o);
-    win[k >> 2] |= (uint32_t) (code << 4) << (8 * (k & 3));
+    const FamDev *__restrict__ F = (p == 0) ? F0 : ((F0->mate >= 0) ? fams + F0->mate : F0);
+    Fp[p] = F;
+    PassRegs<C> &S = ps[p];
+    S.active = (p == 0) || (F0->mate >= 0);
+    const int n_ext = F->n_ext;
+    // balanced partition of the pass's instances over the CTAs of the launch unit
+    const int first = (int) ((long long) cta_in_fam * n_ext / n_ctas);
+    const int next = (int) ((long long) (cta_in_fam + 1) * n_ext / n_ctas);
+    const int grp = warp * IPW + gw;
+    S.valid = S.active && (gw < IPW) && (grp < next - first);
+    S.inst = S.valid ? first + grp : max(min(next, n_ext) - 1, 0);   // other lanes shadow an instance
+    const InstDev I = F->inst[S.inst];
+    S.start = I.start;
+    S.sgn = I.sgn;
+    S.comp = I.comp;
+    S.tmin = I.tmin;
+    S.tmax = I.tmax;
+    dbg_on[p] = (F->dbg_rows != nullptr) || (F->dbg_path != nullptr);
+    use_fast[p] = (WS != 0) && gaps_ok && !dbg_on[p];
+#pragma unroll
+    for (int i = 0; i < CW; ++i)
+      S.win[i] = 0;
+    S.maxD = kNeg;
+    // boundary row S = G = (o == 0 ? 0 : |o| * ge + go), ram_extend.c:909-946
+#pragma unroll
+    for (int k = 0; k < C; ++k)
+    {
+      const int K = K0 + k;
+      const int o = K - B;
+      const int v = (o == 0) ? 0 : abs(o) * ge + go;
+      const int v1 = (o + 1 == 0) ? 0 : abs(o + 1) * ge + go;
+      S.Pp[k] = (K < W) ? v : kNegInf;
+      S.Dd[k] = (K < W - 1) ? imax(v1 + goe, v1 + ge) : (K == W - 1) ? kNeg : kNegInf;
+      S.maxD = imax(S.maxD, S.Dd[k]);
+    }
+#pragma unroll 1
+    for (int k = 0; k < C; ++k)
+    {
+      const int code = fetch_code(F->lib2, F->libn, S.start, S.sgn, S.comp, S.tmin, S.tmax, K0 + k - B);
+      const uint32_t b = (uint32_t) (code << 4) << (8 * (k & 3));
+#pragma unroll
+      for (int i = 0; i < CW; ++i)
+        S.win[i] |= (i == (k >> 2)) ? b : 0u;
+    }
+    // rows in which every lane of this warp has its whole segment inside the sequence bounds, and
+    // the first row from which every band of the warp has left its window for good
+    S.r_fast_lo = __reduce_max_sync(kFull, S.tmin + B - K0);
+    S.r_fast_hi = __reduce_min_sync(kFull, S.tmax + B - K0 - nreal + 1);
+    S.r_dead = max(__reduce_max_sync(kFull, S.tmax) + B + 1, B);
+    S.high = S.pos = S.thigh = S.tpos = 0;
+    S.max_row = -1;
+    S.max_ext = 0;
+    S.stop_row = -1;
+    S.nib_lo = S.nib_hi = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      S.best[a] = kOob;
+    if (L <= 0)
+      S.active = false;
   }
 
-  const int nreal = min(max(W - K0, 0), C);   // real (in-band) cells of this lane
-  // rows in which every lane of this warp has its whole segment inside the sequence bounds, and
-  // the first row from which every band of the warp has left its window for good
-  const int r_fast_lo = __reduce_max_sync(kFull, tmin + B - K0);
-  const int r_fast_hi = __reduce_min_sync(kFull, tmax + B - K0 - nreal + 1);
-  const int r_dead = max(__reduce_max_sync(kFull, tmax) + B + 1, B);
-  const bool use_fast = (WS != 0) && gaps_ok && !dbg_on;
-
 #ifndef RAMCU_EMUL
-  const long long t_begin = F->dbg_wait ? clock64() : 0;
+  const bool stats = (F0->dbg_wait != nullptr);
+  const long long t_begin = stats ? clock64() : 0;
+  long long t_wait = 0;
 #endif
-  int high = 0, pos = 0, thigh = 0, tpos = 0;   // ram_extend.c:900-914
-  int max_row = -1, max_ext = 0, stop_row = -1;
-  uint32_t nib_lo = 0, nib_hi = 0;   // codes of the next band positions entering at the high end
-  int r = 0;
 
-  for (r = 0; r < L; ++r)
-  {
-    const int par = r & 1;
-    if ((r & 15) == 0 && is_last)
-      feed16(lib2, libn, I.start, I.sgn, I.comp, tmin, tmax, r - B + G * C, nib_lo, nib_hi);
-
-    const bool fast = use_fast && (r >= r_fast_lo) && (r <= r_fast_hi);
-    const bool alldead = !dbg_on && (r >= r_dead);   // every cell out of bounds, for good
-
+  // ---- sweep of row r: row best of every candidate base, then the pass's contribution to the
+  //      column sums (ram_extend.c:1042-1062) goes on its way ---------------------------------------
+  auto sweep_and_send = [&](auto pc, const int r) {
+    constexpr int p = decltype(pc)::value;
+    PassRegs<C> &S = ps[p];
+    const FamDev *__restrict__ F = Fp[p];
+    const bool fast = use_fast[p] && (r >= S.r_fast_lo) && (r <= S.r_fast_hi);
+    const bool alldead = !dbg_on[p] && (r >= S.r_dead);   // every cell out of bounds, for good
     int best[4] = {kOob, kOob, kOob, kOob};
-
-    // ---- sweep: row best of every candidate base ---------------------------------------------
     if (!alldead)
     {
 #pragma unroll
@@ -578,15 +576,15 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
 #pragma unroll
         for (int k = 0; k < C; ++k)
         {
-          const int4 m4 = *reinterpret_cast<const int4 *>(lutb + win_byte(win[k >> 2], k & 3));
-          best[0] = imax(best[0], Pp[k] + m4.x);
-          best[1] = imax(best[1], Pp[k] + m4.y);
-          best[2] = imax(best[2], Pp[k] + m4.z);
-          best[3] = imax(best[3], Pp[k] + m4.w);
+          const int4 m4 = *reinterpret_cast<const int4 *>(lutb + win_byte(S.win[k >> 2], k & 3));
+          best[0] = imax(best[0], S.Pp[k] + m4.x);
+          best[1] = imax(best[1], S.Pp[k] + m4.y);
+          best[2] = imax(best[2], S.Pp[k] + m4.z);
+          best[3] = imax(best[3], S.Pp[k] + m4.w);
         }
 #pragma unroll
         for (int a = 0; a < 4; ++a)
-          best[a] = imax(best[a], maxD);
+          best[a] = imax(best[a], S.maxD);
       }
       else if (gaps_ok)
       {
@@ -597,14 +595,14 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
           const int K = K0 + k;
           const bool real = K < W;
           const int t = r - B + K;
-          const bool inb = real && (t >= tmin) && (t <= tmax);
+          const bool inb = real && (t >= S.tmin) && (t <= S.tmax);
           const int E = (K < B && r < B) ? edge : kOob;
-          const int Dk = (K >= W - 1) ? kNeg : Dd[k];
-          const int4 m4 = *reinterpret_cast<const int4 *>(lutb + win_byte(win[k >> 2], k & 3));
-          const int v0 = inb ? imax(Pp[k] + m4.x, Dk) : E;
-          const int v1 = inb ? imax(Pp[k] + m4.y, Dk) : E;
-          const int v2 = inb ? imax(Pp[k] + m4.z, Dk) : E;
-          const int v3 = inb ? imax(Pp[k] + m4.w, Dk) : E;
+          const int Dk = (K >= W - 1) ? kNeg : S.Dd[k];
+          const int4 m4 = *reinterpret_cast<const int4 *>(lutb + win_byte(S.win[k >> 2], k & 3));
+          const int v0 = inb ? imax(S.Pp[k] + m4.x, Dk) : E;
+          const int v1 = inb ? imax(S.Pp[k] + m4.y, Dk) : E;
+          const int v2 = inb ? imax(S.Pp[k] + m4.z, Dk) : E;
+          const int v3 = inb ? imax(S.Pp[k] + m4.w, Dk) : E;
           best[0] = real ? imax(best[0], v0) : best[0];
           best[1] = real ? imax(best[1], v1) : best[1];
           best[2] = real ? imax(best[2], v2) : best[2];
@@ -614,19 +612,22 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       else
       {
         // positive gap penalties: the full row of every candidate, without committing it
-        const bool open = (r - B + K0 >= tmin) && (r - B + K0 + C - 1 <= tmax) && (nreal == C);
+        const bool open = (r - B + K0 >= S.tmin) && (r - B + K0 + C - 1 <= S.tmax) && (nreal == C);
         const RowDbg nodbg = {nullptr, nullptr, 0, false};
 #pragma unroll 1
         for (int a = 0; a < 4; ++a)
         {
           int nob = 0, noi = 0, noh = 0;
-          const int agg = exact_pass<C, false, false>(Pp, Dd, win, lutb, a, go, ge, (gl == 0) ? kNeg : kNegInf, gl, W,
-                                                      B, r, tmin, tmax, nob, 0, noi, noh, nodbg);
+          const int agg = exact_pass<C, false, false>(S.Pp, S.Dd, S.win, lutb, a, go, ge, (gl == 0) ? kNeg : kNegInf,
+                                                      gl, W, B, r, S.tmin, S.tmax, nob, 0, noi, noh, nodbg);
           const int hin = carry_scan_exact<C, G>(agg, open, ge, gl);
           int b = kNeg;
-          exact_pass<C, true, false>(Pp, Dd, win, lutb, a, go, ge, hin, gl, W, B, r, tmin, tmax, b, 0, noi, noh,
-                                     nodbg);
-          best[a] = b;
+          exact_pass<C, true, false>(S.Pp, S.Dd, S.win, lutb, a, go, ge, hin, gl, W, B, r, S.tmin, S.tmax, b, 0, noi,
+                                     noh, nodbg);
+          best[0] = (a == 0) ? b : best[0];
+          best[1] = (a == 1) ? b : best[1];
+          best[2] = (a == 2) ? b : best[2];
+          best[3] = (a == 3) ? b : best[3];
         }
       }
       // row best over the instance's G lanes
@@ -634,89 +635,161 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       for (int a = 0; a < 4; ++a)
         best[a] = group_max<G>(best[a], gl, lane);
     }
-
-    // ---- column sums over the family (ram_extend.c:1042-1062) -------------------------------
-    unsigned sums[4];
-    {
-      const bool lead = valid && (gl == 0);
-      int c[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a)
+      S.best[a] = best[a];
+
+    // contribution of this warp, then of this CTA
+    const bool lead = S.valid && (gl == 0);
+    int c[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+    {
+      c[a] = lead ? imax3(best[a], 0, S.high + cap) : 0;
+      c[a] = __reduce_add_sync(kFull, c[a]);
+    }
+    PassShared &H = sh.ps[p];
+    const int slot = r & 1;
+    int last = 0;
+    if (lane == 0)
+    {
+      if (nwarps > 1)
       {
-        c[a] = lead ? imax3(best[a], 0, high + cap) : 0;
-        c[a] = __reduce_add_sync(kFull, c[a]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          atomicAdd(&H.acc[slot][a], c[a]);
+        __threadfence_block();
+        last = (atomicAdd(&H.cnt[slot], 1) == nwarps - 1) ? 1 : 0;
       }
-      if (lane == 0)
-        s_part[par][warp] = make_int4(c[0], c[1], c[2], c[3]);
-      __syncthreads();
+      else
+        last = 1;
+    }
+    last = __shfl_sync(kFull, last, 0);
+    if (last)
+    {
+      // this warp counted last: it owns the CTA's sums of the column
+      int mine = 0;
+      if (nwarps > 1)
       {
-        const int4 p = (lane < nwarps) ? s_part[par][lane] : make_int4(0, 0, 0, 0);
-        sums[0] = (unsigned) __reduce_add_sync(kFull, p.x);
-        sums[1] = (unsigned) __reduce_add_sync(kFull, p.y);
-        sums[2] = (unsigned) __reduce_add_sync(kFull, p.z);
-        sums[3] = (unsigned) __reduce_add_sync(kFull, p.w);
+        __threadfence_block();
+        if (lane < 4)
+        {
+          mine = ld_volatile_shared(&H.acc[slot][lane]);
+          st_volatile_shared(&H.acc[slot][lane], 0);
+        }
+        if (lane == 0)
+          st_volatile_shared(&H.cnt[slot], 0);
       }
+      else
+        mine = sel4(lane & 3, c[0], c[1], c[2], c[3]);
       if (n_ctas > 1)
       {
-        if (warp == 0)
-        {
-#ifndef RAMCU_EMUL
-          const long long t_ex0 = F->dbg_wait ? clock64() : 0;
-#endif
-          if (n_ctas > kSlotMaxCtas)
-            grid_exchange_red(F->slots + (size_t) r * 4 * kRedStride, n_ctas, sums, lane);
-          else
-            grid_exchange(F->slots, n_ctas, cta_in_fam, par, (unsigned) (r + 1), sums, lane);
-#ifndef RAMCU_EMUL
-          if (F->dbg_wait && lane == 0)
-            F->dbg_wait[2 * cta_in_fam] += clock64() - t_ex0;
-#endif
-          if (lane == 0)
-            s_bcast[par] = make_int4((int) sums[0], (int) sums[1], (int) sums[2], (int) sums[3]);
-        }
-        __syncthreads();
-        const int4 p = s_bcast[par];
-        sums[0] = (unsigned) p.x;
-        sums[1] = (unsigned) p.y;
-        sums[2] = (unsigned) p.z;
-        sums[3] = (unsigned) p.w;
+        if (lane < 4)   // column r owns four accumulators: (arrivals << 48 | sum), zeroed before the launch
+          atomicAdd(F->slots + (size_t) r * 4 * kRedStride + lane * kRedStride,
+                    (1ull << 48) | (unsigned long long) (unsigned) mine);
+      }
+      else
+      {
+        if (lane < 4)
+          st_volatile_shared(&H.res[slot][lane], mine);
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0)
+          st_volatile_shared(&H.res_tag[slot], r + 1);
       }
     }
+  };
 
-    // ---- argmax over the four bases (ram_extend.c:973-974, 1081-1085) ------------------------
+  // ---- the column sums of row r arrive --------------------------------------------------------------
+  auto receive = [&](auto pc, const int r, int (&sums)[4]) {
+    constexpr int p = decltype(pc)::value;
+    const FamDev *__restrict__ F = Fp[p];
+    PassShared &H = sh.ps[p];
+    const int slot = r & 1;
+    if (n_ctas > 1 && warp == 0)
+    {
+#ifndef RAMCU_EMUL
+      const long long t0 = stats ? clock64() : 0;
+#endif
+      unsigned lo = 0;
+      if (lane < 4)
+      {
+        const unsigned long long *word = F->slots + (size_t) r * 4 * kRedStride + lane * kRedStride;
+        unsigned long long v;
+        unsigned spins = 0;
+        do
+        {
+          v = ld_relaxed_u64(word);
+          if (++spins > kMaxGlobalSpins)
+            spin_timeout();   // a CTA of this family never became resident (something else holds the SMs)
+        } while ((int) (v >> 48) != n_ctas);
+        lo = (unsigned) v;
+        st_volatile_shared(&H.res[slot][lane], (int) lo);
+      }
+      __syncwarp();
+      __threadfence_block();
+      if (lane == 0)
+        st_volatile_shared(&H.res_tag[slot], r + 1);
+#ifndef RAMCU_EMUL
+      if (stats)
+        t_wait += clock64() - t0;
+#endif
+    }
+    {
+      unsigned spins = 0;
+      while (ld_volatile_shared(&H.res_tag[slot]) != r + 1)
+        if (++spins > kMaxSharedSpins)
+          spin_timeout();
+    }
+    __threadfence_block();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      sums[a] = ld_volatile_shared(&H.res[slot][a]);
+  };
+
+  // ---- argmax, commit of row r, record / improvement / stop rule, window slide -----------------------
+  auto commit = [&](auto pc, const int r, const int (&sums)[4]) {
+    constexpr int p = decltype(pc)::value;
+    PassRegs<C> &S = ps[p];
+    const FamDev *__restrict__ F = Fp[p];
+    const int n_ext = F->n_ext;
+    if ((r & 15) == 0 && is_last)
+      feed16(F->lib2, F->libn, S.start, S.sgn, S.comp, S.tmin, S.tmax, r - B + G * C, S.nib_lo, S.nib_hi);
+    const bool fast = use_fast[p] && (r >= S.r_fast_lo) && (r <= S.r_fast_hi);
+    const bool alldead = !dbg_on[p] && (r >= S.r_dead);
+
+    // argmax over the four bases (ram_extend.c:973-974, 1081-1085)
     int curr = 0, besta = 0;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
     {
-      if ((int) sums[a] > curr)
+      if (sums[a] > curr)
       {
-        curr = (int) sums[a];
+        curr = sums[a];
         besta = a;
       }
     }
-    if (forced != nullptr)
+    if (F->forced != nullptr)
     {
-      besta = forced[r] & 3;
-      curr = (int) sums[besta];
+      besta = F->forced[r] & 3;
+      curr = sel4(besta, sums[0], sums[1], sums[2], sums[3]);
     }
-
     if (F->dbg_best != nullptr)
     {
-      if (valid && gl == 0)
+      if (S.valid && gl == 0)
       {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
-          F->dbg_best[((size_t) r * n_ext + inst) * 4 + a] = best[a];
+          F->dbg_best[((size_t) r * n_ext + S.inst) * 4 + a] = S.best[a];
       }
       if (cta_in_fam == 0 && threadIdx.x < 4)
-        F->dbg_sums[(size_t) r * 4 + threadIdx.x] =
-          sel4(threadIdx.x, (int) sums[0], (int) sums[1], (int) sums[2], (int) sums[3]);
+        F->dbg_sums[(size_t) r * 4 + threadIdx.x] = sel4(threadIdx.x, sums[0], sums[1], sums[2], sums[3]);
     }
 
-    // ---- commit the chosen base's row (ram_extend.c:1105-1150) -------------------------------
+    // commit the chosen base's row (ram_extend.c:1105-1150)
     if (!alldead)
     {
-      const int bestb = sel4(besta, best[0], best[1], best[2], best[3]);
+      const int bestb = sel4(besta, S.best[0], S.best[1], S.best[2], S.best[3]);
       int idx = kBig;
       if (fast)
       {
@@ -724,7 +797,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         uint32_t wa[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i)
-          wa[i] = win[i] | (0x04040404u * (unsigned) besta);   // LUT offset of m[code][besta]
+          wa[i] = S.win[i] | (0x04040404u * (unsigned) besta);   // LUT offset of m[code][besta]
         unsigned hits[HW];
 #pragma unroll
         for (int i = 0; i < HW; ++i)
@@ -735,15 +808,15 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         for (int k = 0; k < C; ++k)
         {
           const int m = *reinterpret_cast<const int *>(lutb + win_byte(wa[k >> 2], k & 3));
-          const int S = Pp[k] + m;
-          const int y = imax(S + goe, Dd[k] + ge);
-          const int pn = imax3(S, Dd[k], hprev);
+          const int Sv = S.Pp[k] + m;
+          const int y = imax(Sv + goe, S.Dd[k] + ge);
+          const int pn = imax3(Sv, S.Dd[k], hprev);
           const int hn = imax(hprev + ge, y);
-          Pp[k] = pn;
+          S.Pp[k] = pn;
           if (k == 0)
             h0 = hn;
           else
-            Dd[k - 1] = hn;
+            S.Dd[k - 1] = hn;
           hprev = hn;
           if (G == 1 && pn == bestb && k <= kR)
             hits[k >> 5] |= 1u << (k & 31);
@@ -760,23 +833,23 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
             const int pen = (gl >= d) ? d * C * ge : kNegInf;
             agg = imax(agg, __shfl_up_sync(kFull, agg, d) + pen);
           }
-          int c = __shfl_up_sync(kFull, agg, 1);
-          c = (gl > 0) ? c : kNegInf;
+          int cy = __shfl_up_sync(kFull, agg, 1);
+          cy = (gl > 0) ? cy : kNegInf;
           // fold the carry in: cell k sees carry + k * ge, its H carry + (k+1) * ge
 #pragma unroll
           for (int k = 0; k < C; ++k)
           {
-            const int pn = imax(Pp[k], c);
-            Pp[k] = pn;
+            const int pn = imax(S.Pp[k], cy);
+            S.Pp[k] = pn;
             if (pn == bestb && (k <= kR || !is_last))
               hits[k >> 5] |= 1u << (k & 31);
-            c += ge;
+            cy += ge;
             if (k == 0)
-              h0 = imax(h0, c);
+              h0 = imax(h0, cy);
             else
-              Dd[k - 1] = imax(Dd[k - 1], c);
+              S.Dd[k - 1] = imax(S.Dd[k - 1], cy);
           }
-          Dd[C - 1] = __shfl_down_sync(kFull, h0, 1);
+          S.Dd[C - 1] = __shfl_down_sync(kFull, h0, 1);
         }
         // cells right of the band: offset == bandwidth has no deletion, padding cells stay inert
 #pragma unroll
@@ -784,24 +857,24 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         {
           if (G == 1)
           {
-            Dd[k] = (k == kR) ? kNeg : kNegInf;
+            S.Dd[k] = (k == kR) ? kNeg : kNegInf;
             if (k > kR)
-              Pp[k] = kNegInf;
+              S.Pp[k] = kNegInf;
           }
           else
           {
-            Dd[k] = is_last ? ((k == kR) ? kNeg : kNegInf) : Dd[k];
+            S.Dd[k] = is_last ? ((k == kR) ? kNeg : kNegInf) : S.Dd[k];
             if (k > kR)
-              Pp[k] = is_last ? kNegInf : Pp[k];
+              S.Pp[k] = is_last ? kNegInf : S.Pp[k];
           }
         }
         int md = kNeg;
 #pragma unroll
         for (int k = 0; k + 1 < C; k += 2)
-          md = imax3(md, Dd[k], Dd[k + 1]);
+          md = imax3(md, S.Dd[k], S.Dd[k + 1]);
         if (C & 1)
-          md = imax(md, Dd[C - 1]);
-        maxD = md;
+          md = imax(md, S.Dd[C - 1]);
+        S.maxD = md;
 #pragma unroll
         for (int i = HW - 1; i >= 0; --i)
           if (hits[i])
@@ -809,89 +882,133 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       }
       else
       {
-        const bool open = (r - B + K0 >= tmin) && (r - B + K0 + C - 1 <= tmax) && (nreal == C);
+        const bool open = (r - B + K0 >= S.tmin) && (r - B + K0 + C - 1 <= S.tmax) && (nreal == C);
         const RowDbg nodbg = {nullptr, nullptr, 0, false};
-        const RowDbg dbg = {dbg_rows ? dbg_rows + (size_t) r * n_ext * W * 2 : nullptr,
-                            dbg_path ? dbg_path + (size_t) r * n_ext * W : nullptr, inst, valid};
+        const RowDbg dbg = {F->dbg_rows ? F->dbg_rows + (size_t) r * n_ext * W * 2 : nullptr,
+                            F->dbg_path ? F->dbg_path + (size_t) r * n_ext * W : nullptr, S.inst, S.valid};
         int nob = 0, noi = 0, h0 = 0;
-        const int agg = exact_pass<C, false, false>(Pp, Dd, win, lutb, besta, go, ge, (gl == 0) ? kNeg : kNegInf, gl,
-                                                    W, B, r, tmin, tmax, nob, 0, noi, h0, nodbg);
+        const int agg = exact_pass<C, false, false>(S.Pp, S.Dd, S.win, lutb, besta, go, ge, (gl == 0) ? kNeg : kNegInf,
+                                                    gl, W, B, r, S.tmin, S.tmax, nob, 0, noi, h0, nodbg);
         const int hin = carry_scan_exact<C, G>(agg, open, ge, gl);
-        exact_pass<C, true, true>(Pp, Dd, win, lutb, besta, go, ge, hin, gl, W, B, r, tmin, tmax, nob, bestb, idx,
-                                  h0, dbg);
-        Dd[C - 1] = (G > 1) ? __shfl_down_sync(kFull, h0, 1) : kNeg;
+        exact_pass<C, true, true>(S.Pp, S.Dd, S.win, lutb, besta, go, ge, hin, gl, W, B, r, S.tmin, S.tmax, nob, bestb,
+                                  idx, h0, dbg);
+        S.Dd[C - 1] = (G > 1) ? __shfl_down_sync(kFull, h0, 1) : kNeg;
         int md = kNeg;
 #pragma unroll
         for (int k = 0; k < C; ++k)
         {
           const int K = K0 + k;
-          Dd[k] = (K < W - 1) ? Dd[k] : (K == W - 1) ? kNeg : kNegInf;
-          md = imax(md, Dd[k]);
+          S.Dd[k] = (K < W - 1) ? S.Dd[k] : (K == W - 1) ? kNeg : kNegInf;
+          md = imax(md, S.Dd[k]);
         }
-        maxD = md;
+        S.maxD = md;
       }
       int kidx = (idx < kBig) ? K0 + idx : kBig;
       kidx = group_min<G>(kidx, gl, lane);
-      if (bestb > high)   // record setter, ram_extend.c:1140-1150
+      if (bestb > S.high)   // record setter, ram_extend.c:1140-1150
       {
-        high = bestb;
-        pos = r - B + kidx;
+        S.high = bestb;
+        S.pos = r - B + kidx;
       }
-      if (dbg_path != nullptr && valid && gl == 0)
-        F->dbg_idx[(size_t) r * n_ext + inst] = kidx;
+      if (F->dbg_path != nullptr && S.valid && gl == 0)
+        F->dbg_idx[(size_t) r * n_ext + S.inst] = kidx;
     }
 
-    // ---- improvement / stop rule (ram_extend.c:1194-1223) ------------------------------------
-    if (curr >= max_ext + abs(max_row - r) * minimp)
+    // improvement / stop rule (ram_extend.c:1194-1223)
+    if (curr >= S.max_ext + abs(S.max_row - r) * minimp)
     {
-      max_row = r;
-      max_ext = curr;
-      thigh = high;
-      tpos = pos;
+      S.max_row = r;
+      S.max_ext = curr;
+      S.thigh = S.high;
+      S.tpos = S.pos;
     }
     if (cta_in_fam == 0 && threadIdx.x == 0)
       F->master[r] = (unsigned char) besta;
-    if (r - max_row >= stop)
+    if (r - S.max_row >= stop)
     {
-      stop_row = r;
-      break;
+      S.stop_row = r;
+      S.active = false;
     }
-
-    // ---- slide the base window by one band position ------------------------------------------
+    else if (r + 1 >= L)
+      S.active = false;
+    if (S.active)
     {
-      uint32_t in = (nib_lo << 4) & 0xf0u;
-      nib_lo = __funnelshift_r(nib_lo, nib_hi, 4);
-      nib_hi >>= 4;
+      // slide the base window by one band position
+      uint32_t in = (S.nib_lo << 4) & 0xf0u;
+      S.nib_lo = __funnelshift_r(S.nib_lo, S.nib_hi, 4);
+      S.nib_hi >>= 4;
       if (G > 1)
       {
-        const uint32_t nb = __shfl_down_sync(kFull, win[0] & 0xffu, 1);
+        const uint32_t nb = __shfl_down_sync(kFull, S.win[0] & 0xffu, 1);
         in = is_last ? in : nb;
       }
 #pragma unroll
       for (int i = 0; i + 1 < CW; ++i)
-        win[i] = __funnelshift_r(win[i], win[i + 1], 8);
-      win[CW - 1] >>= 8;
-      win[(C - 1) >> 2] |= in << (8 * ((C - 1) & 3));
+        S.win[i] = __funnelshift_r(S.win[i], S.win[i + 1], 8);
+      S.win[CW - 1] >>= 8;
+      S.win[(C - 1) >> 2] |= in << (8 * ((C - 1) & 3));
     }
+  };
+
+  // ---- column loop: the passes take turns, so that the exchange of one pass's column sums is in
+  //      flight while the other pass's row is computed --------------------------------------------------
+  if (ps[0].active)
+    sweep_and_send(PassTag<0>(), 0);
+  if (NP > 1 && ps[NP - 1].active)
+    sweep_and_send(PassTag<NP - 1>(), 0);
+  for (int r = 0; r < L; ++r)
+  {
+    bool any = false;
+    if (ps[0].active)
+    {
+      int sums[4];
+      receive(PassTag<0>(), r, sums);
+      commit(PassTag<0>(), r, sums);
+      if (ps[0].active)
+        sweep_and_send(PassTag<0>(), r + 1);
+      any = true;
+    }
+    if (NP > 1 && ps[NP - 1].active)
+    {
+      int sums[4];
+      receive(PassTag<NP - 1>(), r, sums);
+      commit(PassTag<NP - 1>(), r, sums);
+      if (ps[NP - 1].active)
+        sweep_and_send(PassTag<NP - 1>(), r + 1);
+      any = true;
+    }
+    if (!any)
+      break;
   }
 
-#ifndef RAMCU_EMUL
-  if (F->dbg_wait && threadIdx.x == 0)
-    F->dbg_wait[2 * cta_in_fam + 1] = clock64() - t_begin;
-#endif
   // ---- write back (ram_extend.c:1234-1257) ---------------------------------------------------
-  if (valid && gl == 0)
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
   {
-    F->thigh[inst] = thigh;
-    F->tpos[inst] = tpos;
+    if (p > 0 && F0->mate < 0)
+      continue;
+    const FamDev *__restrict__ F = Fp[p];
+    const PassRegs<C> &S = ps[p];
+    if (S.valid && gl == 0)
+    {
+      F->thigh[S.inst] = S.thigh;
+      F->tpos[S.inst] = S.tpos;
+    }
+    if (cta_in_fam == 0 && threadIdx.x == 0)
+    {
+      F->result[0] = S.max_row;
+      F->result[1] = (S.stop_row >= 0) ? S.stop_row + 1 : L;
+      F->result[2] = S.stop_row;
+      F->result[3] = S.max_ext;
+    }
   }
-  if (cta_in_fam == 0 && threadIdx.x == 0)
+#ifndef RAMCU_EMUL
+  if (stats && threadIdx.x == 0)
   {
-    F->result[0] = max_row;
-    F->result[1] = (stop_row >= 0) ? stop_row + 1 : L;
-    F->result[2] = stop_row;
-    F->result[3] = max_ext;
+    F0->dbg_wait[2 * cta_in_fam] = t_wait;
+    F0->dbg_wait[2 * cta_in_fam + 1] = clock64() - t_begin;
   }
+#endif
 }
 
 }  // namespace ramcu

@@ -13,22 +13,40 @@ struct KernelCfg
   int B;    // bandwidth this instantiation is specialised for (-1 = any, runtime W)
   int C;    // cells per lane
   int G;    // lanes per instance
-  int maxt; // largest CTA size (threads) supported; caps registers per thread at 65536 / maxt
-  extend_fn fn;
-  int regs; // filled at init
+  // [0]: one pass per CTA; [1]: the right and the left pass of a family in the same threads (NULL
+  // when the two row states do not fit the register file)
+  int maxt[2];      // largest CTA size (threads); caps registers per thread at 65536 / maxt
+  extend_fn fn[2];
+  int regs[2];      // filled at init
 };
 
 // MAXT: wide lanes keep the whole 255-register budget (no spills); narrow lanes trade registers
-// for more resident warps.
+// for more resident warps. Two passes per thread hold two row states.
 constexpr int maxt_for(int C)
 {
   return C <= 8 ? 768 : C <= 13 ? 512 : C <= 20 ? 384 : 256;
 }
-#define RAMCU_CFG(B_, C_, G_) {B_, C_, G_, maxt_for(C_), extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_)>, 0}
+constexpr int maxt2_for(int C)
+{
+  return C <= 6 ? 768 : C <= 11 ? 512 : C <= 19 ? 384 : 256;
+}
+#define RAMCU_CFG(B_, C_, G_)                                                                              \
+  {B_, C_, G_, {maxt_for(C_), maxt2_for(C_)},                                                              \
+   {extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1>, extend_kernel<C_, G_, 2 * B_ + 1, maxt2_for(C_), 2>}, \
+   {0, 0}}
+// wide lanes: one pass per CTA only
+#define RAMCU_CFG1(B_, C_, G_) \
+  {B_, C_, G_, {maxt_for(C_), 0}, {extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1>, nullptr}, {0, 0}}
 // same tiling with an explicit (larger) CTA limit: fewer registers per thread, more resident
 // instances -- the capacity fallback for very large families with wide bands
-#define RAMCU_CFG_T(B_, C_, G_, T_) {B_, C_, G_, T_, extend_kernel<C_, G_, 2 * B_ + 1, T_>, 0}
-#define RAMCU_GEN(C_, G_) {-1, C_, G_, maxt_for(C_), extend_kernel<C_, G_, 0, maxt_for(C_)>, 0}
+#define RAMCU_CFG_T(B_, C_, G_, T_) \
+  {B_, C_, G_, {T_, 0}, {extend_kernel<C_, G_, 2 * B_ + 1, T_, 1>, nullptr}, {0, 0}}
+#define RAMCU_GEN(C_, G_)                                                                \
+  {-1, C_, G_, {maxt_for(C_), maxt2_for(C_)},                                            \
+   {extend_kernel<C_, G_, 0, maxt_for(C_), 1>, extend_kernel<C_, G_, 0, maxt2_for(C_), 2>}, \
+   {0, 0}}
+#define RAMCU_GEN1(C_, G_) \
+  {-1, C_, G_, {maxt_for(C_), 0}, {extend_kernel<C_, G_, 0, maxt_for(C_), 1>, nullptr}, {0, 0}}
 
 struct CfgList
 {

@@ -5,7 +5,6 @@ namespace ramcu {
 
 static KernelCfg g_list[] = {
   RAMCU_CFG(14, 29, 1), RAMCU_CFG(14, 15, 2), RAMCU_CFG(14, 10, 3), RAMCU_CFG(14, 8, 4), RAMCU_CFG(14, 4, 8),
-  RAMCU_CFG_T(14, 29, 1, 512), RAMCU_CFG_T(14, 15, 2, 512),
 };
 
 CfgList cfgs_b14() { return CfgList{g_list, (int) (sizeof(g_list) / sizeof(g_list[0]))}; }

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -77,13 +78,19 @@ static void collect_cfgs()
 // ------------------------------------------------------------------------------------------
 // objects
 // ------------------------------------------------------------------------------------------
+constexpr int kTickets = 256;   // ring of launch tickets: a launch keeps its own word while it runs
+
 struct ramcu_ctx
 {
   int device;
   int sm_count, cc_major, cc_minor;
   cudaStream_t own_stream, stream;
   cudaEvent_t ev0, ev1;
-  int *d_ticket;
+  int *d_ticket;            // kTickets words
+  unsigned ticket_next;
+  unsigned long long launch_gen;   // ev0/ev1 belong to the jobs timed in this generation
+  bool coop_ok;             // cudaDevAttrCooperativeLaunch
+  std::map<size_t, std::vector<void *>> pinned_free;   // pinned result blocks, by size class
 };
 
 struct ramcu_library
@@ -100,30 +107,42 @@ struct ramcu_job
   int direction, n_cores, n_ext;
   ramcu_scoring_t sc;
   ramcu_params_t pr;
-  const KernelCfg *cfg;
-  int n_ctas;                 // > 0 when there is anything to launch (== solo.n_ctas)
-  Plan solo;                  // layout for ramcu_job_run
-  int batch_ctas;             // layout for ramcu_batch_run (kBatchThreads per CTA)
+  const KernelCfg *cfg = nullptr;
+  int n_ctas = 0;             // > 0 when there is anything to launch (== solo.n_ctas)
+  Plan solo = {0, 0};         // layout for ramcu_job_run
+  int batch_ctas = 0;         // layout for ramcu_batch_run (batch_threads() per CTA)
+  int max_ctas = 0;           // size of d_cta_fam / d_dbg_wait
+  // the family's other pass (ramcu_job_create_pair) and the layout of both passes in the same threads
+  ramcu_job *mate = nullptr;
+  const KernelCfg *pair_cfg = nullptr;
+  Plan pair_solo = {0, 0};
+  int pair_batch_ctas = 0;
   std::vector<int> orig;      // ext index -> core index
   FamDev fam;                 // host copy (device pointers inside)
+  bool fam_dirty = false;     // d_fam no longer holds the solo layout
   // device
-  InstDev *d_inst;
-  unsigned char *d_master;
-  int *d_thigh, *d_tpos, *d_result;
-  unsigned long long *d_slots;
-  FamDev *d_fam;      // single-family launch
-  int *d_cta_fam;     // zeros, n_ctas
-  unsigned char *d_forced;
-  int *d_dbg_rows, *d_dbg_best, *d_dbg_sums;
-  unsigned char *d_dbg_path;   // -outmat mode (negative dbg_rows in job_create_impl)
-  int *d_dbg_del, *d_dbg_idx;
-  long long *d_dbg_wait;   // RAMCU_STATS=1 diagnostics
-  bool ran, timed;
+  InstDev *d_inst = nullptr;
+  unsigned char *d_out = nullptr;   // [8 ints result][thigh n_ext][tpos n_ext][master L bytes]
+  unsigned char *h_out = nullptr;   // pinned host copy, filled in stream order behind every launch
+  size_t h_out_cap = 0;
+  unsigned long long *d_slots = nullptr;
+  FamDev *d_fam = nullptr;    // single-family launch
+  int *d_cta_fam = nullptr;   // zeros
+  unsigned char *d_forced = nullptr;
+  int *d_dbg_rows = nullptr, *d_dbg_best = nullptr, *d_dbg_sums = nullptr;
+  unsigned char *d_dbg_path = nullptr;   // -outmat mode (negative dbg_rows in job_create_impl)
+  int *d_dbg_idx = nullptr;
+  long long *d_dbg_wait = nullptr;   // RAMCU_STATS=1 diagnostics
+  const KernelCfg *ran_cfg = nullptr;
+  int stats_ctas = 0;
+  bool ran = false, in_batch = false;
+  unsigned long long timed_gen = 0;
 };
 
 // ------------------------------------------------------------------------------------------
 // basic entry points
 // ------------------------------------------------------------------------------------------
+extern "C" void ramcu_destroy(ramcu_ctx *c);
 extern "C" const char *ramcu_last_error(void) { return g_err; }
 extern "C" int ramcu_abi_version(void) { return RAMCU_ABI_VERSION; }
 
@@ -150,7 +169,14 @@ extern "C" int ramcu_init(int device, ramcu_ctx **out)
   c->stream = c->own_stream;
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
-  CK(cudaMalloc(&c->d_ticket, sizeof(int)));
+  CK(cudaMalloc(&c->d_ticket, kTickets * sizeof(int)));
+  c->ticket_next = 0;
+  c->launch_gen = 0;
+  {
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    c->coop_ok = coop != 0;
+  }
   {
     // per-call buffers come from the stream-ordered pool; keep freed memory cached in the pool
     cudaMemPool_t pool;
@@ -160,18 +186,21 @@ extern "C" int ramcu_init(int device, ramcu_ctx **out)
   }
   collect_cfgs();
   for (KernelCfg *k : g_cfgs)
-  {
-    cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, (const void *) k->fn);
-    if (e != cudaSuccess)
+    for (int np = 0; np < 2; ++np)
     {
-      delete c;
-      return fail(RAMCU_ERR_CUDA,
-                  "ramcu_init: kernel image not loadable on this device (built for sm_100a): %s",
-                  cudaGetErrorString(e));
+      if (!k->fn[np])
+        continue;
+      cudaFuncAttributes fa;
+      e = cudaFuncGetAttributes(&fa, (const void *) k->fn[np]);
+      if (e != cudaSuccess)
+      {
+        ramcu_destroy(c);
+        return fail(RAMCU_ERR_CUDA,
+                    "ramcu_init: kernel image not loadable on this device (built for sm_100a): %s",
+                    cudaGetErrorString(e));
+      }
+      k->regs[np] = fa.numRegs;
     }
-    k->regs = fa.numRegs;
-  }
   *out = c;
   return RAMCU_OK;
 }
@@ -183,6 +212,9 @@ extern "C" void ramcu_destroy(ramcu_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_ticket);
+  for (auto &kv : c->pinned_free)
+    for (void *p : kv.second)
+      cudaFreeHost(p);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->own_stream);
@@ -288,10 +320,14 @@ static int library_pack(ramcu_ctx *c, const uint8_t *d_bytes, uint64_t length, r
   const size_t pad = 4;                           // words of slack on both sides
   CK(cudaMallocAsync(&lib->alloc2, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t), c->stream));
   CK(cudaMallocAsync(&lib->allocn, (n_chunks + 2 * pad) * sizeof(uint32_t), c->stream));
-  CK(cudaMemsetAsync(lib->alloc2, 0, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t), c->stream));
-  CK(cudaMemsetAsync(lib->allocn, 0xff, (n_chunks + 2 * pad) * sizeof(uint32_t), c->stream));
   lib->d_lib2 = (uint32_t *) lib->alloc2 + pad;
   lib->d_libn = (uint32_t *) lib->allocn + pad;
+  // the kernels write every word of [0, n_chunks); only the slack on both sides is initialised here
+  // (bases: A, mask: N)
+  CK(cudaMemsetAsync(lib->alloc2, 0, pad * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(lib->d_lib2 + n_chunks * 2, 0, pad * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(lib->allocn, 0xff, pad * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(lib->d_libn + n_chunks, 0xff, pad * sizeof(uint32_t), c->stream));
   if (n_chunks > 0)
   {
     const unsigned long long want = (n_chunks + 255) / 256;
@@ -365,13 +401,16 @@ extern "C" int ramcu_library_from_twobit(ramcu_ctx *c, const uint8_t *blob, uint
   unsigned long long *d_ns = nullptr, *d_nl = nullptr;
   CK(cudaMallocAsync(&lib->alloc2, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t), c->stream));
   CK(cudaMallocAsync(&lib->allocn, (n_chunks + 2 * pad) * sizeof(uint32_t), c->stream));
-  CK(cudaMemsetAsync(lib->alloc2, 0, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t), c->stream));
-  CK(cudaMemsetAsync(lib->allocn, 0xff, (n_chunks + 2 * pad) * sizeof(uint32_t), c->stream));
   lib->d_lib2 = (uint32_t *) lib->alloc2 + pad;
   lib->d_libn = (uint32_t *) lib->allocn + pad;
+  CK(cudaMemsetAsync(lib->alloc2, 0, pad * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(lib->d_lib2 + n_chunks * 2, 0, pad * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(lib->allocn, 0xff, pad * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(lib->d_libn + n_chunks, 0xff, pad * sizeof(uint32_t), c->stream));
   if (n_chunks > 0)
   {
-    // the tail bits of the last mask word stay set (positions past the library read as N)
+    // every word of lib2 is written by the decode kernels; the mask starts empty and the N ranges
+    // (and the positions past the library inside the last word) are OR-ed in
     CK(cudaMemsetAsync(lib->d_libn, 0, n_chunks * sizeof(uint32_t), c->stream));
     CK(cudaMallocAsync(&d_blob, blob_bytes ? blob_bytes : 1, c->stream));
     CK(cudaMemcpyAsync(d_blob, blob, blob_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -382,17 +421,18 @@ extern "C" int ramcu_library_from_twobit(ramcu_ctx *c, const uint8_t *blob, uint
     // groups of 128 bases that are not inside one window: at most one per window boundary + the tail
     unsigned long long *d_slow = nullptr;
     unsigned int *d_nslow = nullptr;
-    CK(cudaMallocAsync(&d_slow, ((size_t) n_windows + 4) * sizeof(unsigned long long), c->stream));
+    const unsigned int slow_cap = 2u * (unsigned int) n_windows + 8u;
+    CK(cudaMallocAsync(&d_slow, (size_t) slow_cap * sizeof(unsigned long long), c->stream));
     CK(cudaMallocAsync(&d_nslow, sizeof(unsigned int), c->stream));
     CK(cudaMemsetAsync(d_nslow, 0, sizeof(unsigned int), c->stream));
     twobit_windows_kernel<<<grid, 256, 0, c->stream>>>(d_blob, blob_bytes, d_win, n_windows, total,
-                                                       lib->d_lib2, n_chunks, d_slow, d_nslow);
+                                                       lib->d_lib2, n_chunks, d_slow, d_nslow, slow_cap);
     CK(cudaGetLastError());
     {
-      const unsigned long long wantb = (4ull * ((unsigned long long) n_windows + 4) + 127) / 128;
+      const unsigned long long wantb = (4ull * slow_cap + 127) / 128;
       const int gridb = (int) std::min<unsigned long long>(wantb, (unsigned long long) c->sm_count * 16);
       twobit_boundary_kernel<<<gridb, 128, 0, c->stream>>>(d_blob, blob_bytes, d_win, n_windows, total,
-                                                           lib->d_lib2, n_chunks, d_slow, d_nslow);
+                                                           lib->d_lib2, n_chunks, d_slow, d_nslow, slow_cap);
       CK(cudaGetLastError());
     }
     CK(cudaFreeAsync(d_slow, c->stream));
@@ -400,15 +440,8 @@ extern "C" int ramcu_library_from_twobit(ramcu_ctx *c, const uint8_t *blob, uint
     // positions past `total` inside the last chunk are N
     if (total & 31)
     {
-      const unsigned long long s0 = total, l0 = 32 - (total & 31);
-      CK(cudaMallocAsync(&d_ns, 2 * sizeof(unsigned long long), c->stream));
-      const unsigned long long tail[2] = {s0, l0};
-      CK(cudaMemcpyAsync(d_ns, tail, sizeof(tail), cudaMemcpyHostToDevice, c->stream));
-      nmask_ranges_kernel<<<1, 128, 0, c->stream>>>(d_ns, d_ns + 1, 1, lib->d_libn);
+      nmask_one_range_kernel<<<1, 32, 0, c->stream>>>(total, 32 - (total & 31), lib->d_libn);
       CK(cudaGetLastError());
-      CK(cudaStreamSynchronize(c->stream));   // `tail` is on the stack
-      CK(cudaFreeAsync(d_ns, c->stream));
-      d_ns = nullptr;
     }
     if (n_nranges > 0)
     {
@@ -465,23 +498,30 @@ extern "C" int ramcu_library_free(ramcu_ctx *c, ramcu_library *lib)
 // ------------------------------------------------------------------------------------------
 // jobs
 // ------------------------------------------------------------------------------------------
-static int ctas_per_sm(const KernelCfg *k, int threads)
+// np: 0 = one pass per CTA, 1 = both passes of a family in the same threads
+static int ctas_per_sm(const KernelCfg *k, int np, int threads)
 {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *) k->fn, threads, 0) != cudaSuccess)
+  if (!k->fn[np] ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *) k->fn[np], threads, 0) != cudaSuccess)
     return 0;
   return nb;
 }
 
-// Layout of one family launched on its own: a single CTA when it fits (no grid exchange at all),
-// else 4-warp CTAs on distinct SMs, else the same number of equally loaded CTAs on every SM (the
-// column time is set by the most loaded scheduler, and every CTA of the family waits for it).
-static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int n_ext, Plan *p)
+static int batch_threads(const KernelCfg *k, int np) { return std::min(kBatchThreads, k->maxt[np]); }
+
+// Layout of one launch unit (a pass, or the two passes of a family) launched on its own: a single
+// CTA when it fits (no grid exchange at all), else 4-warp CTAs on distinct SMs, else the same number
+// of equally loaded CTAs on every SM (the column time is set by the most loaded scheduler, and
+// every CTA of the family waits for it).
+static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext, Plan *p)
 {
   const int ipw = inst_per_warp(k->G);
   const long long warps = ((long long) n_ext + ipw - 1) / ipw;
   const int sm = c->sm_count;
-  if (warps * 32 <= k->maxt)
+  if (!k->fn[np])
+    return false;
+  if (warps * 32 <= k->maxt[np])
   {
     p->n_ctas = 1;
     p->threads = (int) warps * 32;
@@ -491,7 +531,7 @@ static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int n_ext, Plan *p
   {
     p->n_ctas = (int) std::min<long long>((warps + 3) / 4, n_ext);
     p->threads = cta_threads(n_ext, p->n_ctas, k->G);
-    return p->threads <= k->maxt;
+    return p->threads <= k->maxt[np];
   }
   for (int per_sm = 1; per_sm <= 16; ++per_sm)
   {
@@ -499,9 +539,9 @@ static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int n_ext, Plan *p
     if (n > n_ext)
       break;
     const int t = cta_threads(n_ext, (int) n, k->G);
-    if (t > k->maxt)
+    if (t > k->maxt[np])
       continue;
-    if (ctas_per_sm(k, t) < per_sm)
+    if (ctas_per_sm(k, np, t) < per_sm)
       continue;
     p->n_ctas = (int) n;
     p->threads = t;
@@ -510,49 +550,55 @@ static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int n_ext, Plan *p
   return false;
 }
 
-// Layout when the family shares a launch with others: fixed CTA size.
-static bool plan_batch(const ramcu_ctx *c, const KernelCfg *k, int n_ext, int *n_ctas)
+// Layout when the unit shares a launch with others: fixed CTA size.
+static bool plan_batch(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext, int *n_ctas)
 {
-  const int per_cta = (kBatchThreads / 32) * inst_per_warp(k->G);
+  if (!k->fn[np])
+    return false;
+  const int threads = batch_threads(k, np);
+  const int per_cta = (threads / 32) * inst_per_warp(k->G);
   const long long n = ((long long) n_ext + per_cta - 1) / per_cta;
-  if (n > (long long) ctas_per_sm(k, kBatchThreads) * c->sm_count)
+  if (n > (long long) ctas_per_sm(k, np, threads) * c->sm_count)
     return false;   // its CTAs could not all be resident: the column exchange would deadlock
   *n_ctas = (int) n;
   return true;
 }
 
-// Rough cycles per column of a family running alone (tuned on B200): a warp
-// executes about C*35 + 450 instructions per row; one warp alone issues one every ~4.5 cycles
-// (dependent max-plus chains), a loaded scheduler one every ~2.2 cycles; the busiest of the
-// four schedulers of the busiest SM sets the pace.
-static double solo_cost(const ramcu_ctx *c, const KernelCfg *k, int n_ext, const Plan &p)
+// Rough cycles per column of a unit running alone (tuned on B200): a warp executes
+// about C*18 + 320 instructions per row and pass (C*15 + 250 when one lane holds the whole band);
+// one warp alone issues one every ~3 cycles (dependent max-plus chains), a loaded scheduler one
+// every ~1.8 cycles; the busiest of the four schedulers of the busiest SM sets the pace.
+static double solo_cost(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext, const Plan &p)
 {
-  // a tiling squeezed below ~6 registers per cell keeps part of its rows in local memory
-  const double squeeze = (65536.0 / k->maxt) < 6.0 * k->C + 60.0 ? 1.5 : 1.0;
-  const double instr = (k->C * 35.0 + 450.0) * squeeze;
+  const double passes = np ? 2.0 : 1.0;
+  // a tiling squeezed below ~2.4 registers per cell and pass keeps part of its rows in local memory
+  const double need = passes * (2.3 * k->C + 30.0) + 40.0;
+  const double squeeze = (65536.0 / k->maxt[np]) < need ? 1.5 : 1.0;
+  const double instr = passes * ((k->G == 1 ? k->C * 15.0 + 250.0 : k->C * 18.0 + 320.0)) * squeeze;
   const int warps_per_cta = p.threads / 32;
   const int ctas_on_sm = (p.n_ctas + c->sm_count - 1) / c->sm_count;
   const double per_sched = std::ceil(warps_per_cta * ctas_on_sm / 4.0);
-  const double sync = p.n_ctas > 1 ? 2000.0 : 0.0;
+  // one pass per CTA waits for every column's exchange; two passes hide each other's
+  const double sync = p.n_ctas > 1 ? (np ? 600.0 : 2400.0) : 0.0;
   (void) n_ext;
-  return std::max(instr * 4.5, per_sched * instr * 2.2) + sync;
+  return std::max(instr * 3.0, per_sched * instr * 1.8) + sync;
 }
 
-static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force_G,
+static const KernelCfg *pick_cfg(const ramcu_ctx *c, int np, int B, int n_ext, int force_G,
                                  int concurrent_instances, int force_maxt, Plan *solo, int *batch_ctas)
 {
   const int W = 2 * B + 1;
   std::vector<const KernelCfg *> cand;
   for (const KernelCfg *k : g_cfgs)
-    if (k->B == B)
+    if (k->B == B && k->fn[np])
       cand.push_back(k);
   if (cand.empty())
     for (const KernelCfg *k : g_cfgs)
-      if (k->B < 0 && k->C * k->G >= W && (k->G - 1) * k->C < W)
+      if (k->B < 0 && k->fn[np] && k->C * k->G >= W && (k->G - 1) * k->C < W)
         cand.push_back(k);
   if (cand.empty())
     for (const KernelCfg *k : g_cfgs)  // narrow bands: trailing lanes may be entirely padding
-      if (k->B < 0 && k->C * k->G >= W)
+      if (k->B < 0 && k->fn[np] && k->C * k->G >= W)
       {
         cand.push_back(k);
         break;
@@ -564,21 +610,22 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force
   const bool crowded = concurrent_instances >= c->sm_count * 128;
   bool have_maxt = false;   // cta_thread_limit is a preference: ignored when no tiling of this band has it
   for (const KernelCfg *k : cand)
-    have_maxt = have_maxt || (k->maxt == force_maxt && (force_G <= 0 || k->G == force_G));
+    have_maxt = have_maxt || (k->maxt[np] == force_maxt && (force_G <= 0 || k->G == force_G));
   for (const KernelCfg *k : cand)
   {
     if (force_G > 0 && k->G != force_G)
       continue;
-    if (force_maxt > 0 && k->maxt != force_maxt && have_maxt)
+    if (force_maxt > 0 && k->maxt[np] != force_maxt && have_maxt)
       continue;
     Plan p;
     int nb = 0;
-    if (!plan_solo(c, k, n_ext, &p))
+    if (!plan_solo(c, k, np, n_ext, &p))
       continue;
-    if (!plan_batch(c, k, n_ext, &nb))
+    if (!plan_batch(c, k, np, n_ext, &nb))
       nb = 0;   // too large to share a launch: ramcu_batch_run launches it on its own
     // a crowded device is throughput bound: fewest lanes per instance = fewest instructions
-    const double cost = crowded ? (double) k->G + (k->maxt > maxt_for(k->C) ? 0.5 : 0.0) : solo_cost(c, k, n_ext, p);
+    const double cost = crowded ? (double) k->G + (k->maxt[np] > (np ? maxt2_for(k->C) : maxt_for(k->C)) ? 0.5 : 0.0)
+                                : solo_cost(c, k, np, n_ext, p);
     if (!best || cost < best_cost)
     {
       best = k;
@@ -590,17 +637,43 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int B, int n_ext, int force
   return best;
 }
 
-static size_t slots_bytes(int n_ctas, int L)
+static size_t slots_bytes(int L) { return ((size_t) L + 1) * 4 * kRedStride * sizeof(unsigned long long); }
+
+// results block of a job, on the device and (pinned) on the host: [8 ints][thigh n_ext][tpos n_ext][master L bytes]
+static size_t out_bytes(int n_ext, int L) { return (8 + 2 * (size_t) n_ext) * sizeof(int) + (size_t) std::max(L, 1); }
+
+static void *pinned_get(ramcu_ctx *c, size_t bytes, size_t *cap)
 {
-  const size_t words = n_ctas > kSlotMaxCtas ? ((size_t) L + 1) * 4 * kRedStride : (size_t) 2 * std::max(n_ctas, 1) * 4;
-  return words * sizeof(unsigned long long);
+  size_t cls = 4096;
+  while (cls < bytes)
+    cls <<= 1;
+  *cap = cls;
+  auto &fl = c->pinned_free[cls];
+  if (!fl.empty())
+  {
+    void *p = fl.back();
+    fl.pop_back();
+    return p;
+  }
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, cls, cudaHostAllocDefault) != cudaSuccess)
+    return nullptr;
+  return p;
+}
+static void pinned_put(ramcu_ctx *c, void *p, size_t cap)
+{
+  if (!p)
+    return;
+  if (c)
+    c->pinned_free[cap].push_back(p);
+  else
+    cudaFreeHost(p);
 }
 
 static void free_job_device(ramcu_ctx *c, ramcu_job *j)
 {
-  void *ptrs[] = {j->d_inst, j->d_master, j->d_thigh, j->d_tpos, j->d_result, j->d_slots, j->d_fam,
-                  j->d_cta_fam, j->d_forced, j->d_dbg_rows, j->d_dbg_best, j->d_dbg_sums, j->d_dbg_wait,
-                  j->d_dbg_path, j->d_dbg_del, j->d_dbg_idx};
+  void *ptrs[] = {j->d_inst, j->d_out, j->d_slots, j->d_fam, j->d_cta_fam, j->d_forced, j->d_dbg_rows,
+                  j->d_dbg_best, j->d_dbg_sums, j->d_dbg_wait, j->d_dbg_path, j->d_dbg_idx};
   for (void *p : ptrs)
     if (p)
     {
@@ -609,7 +682,35 @@ static void free_job_device(ramcu_ctx *c, ramcu_job *j)
       else
         cudaFree(p);
     }
+  pinned_put(c, j->h_out, j->h_out_cap);
+  j->h_out = nullptr;
 }
+
+static void destroy_job(ramcu_ctx *c, ramcu_job *j)
+{
+  if (!j)
+    return;
+  if (j->mate)
+  {
+    j->mate->mate = nullptr;
+    j->mate->pair_cfg = nullptr;
+  }
+  free_job_device(c, j);
+  delete j;
+}
+
+// CUDA call inside job creation: on failure the half-built job and its buffers are released
+#define CKJ(call)                                                                        \
+  do                                                                                     \
+  {                                                                                      \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+    {                                                                                    \
+      destroy_job(c, j);                                                                 \
+      return fail(RAMCU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                   \
+    }                                                                                    \
+  } while (0)
 
 static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
                            const ramcu_core_t *cores, const ramcu_scoring_t *sc,
@@ -647,8 +748,6 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
   j->n_cores = n_cores;
   j->sc = *sc;
   j->pr = *pr;
-  j->ran = false;
-  j->timed = false;
 
   const int B = pr->bandwidth;
   std::vector<InstDev> inst;
@@ -658,82 +757,84 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
   for (size_t i = 0; i < inst.size(); ++i)
     j->orig[i] = inst[i].orig;
 
-  j->cfg = nullptr;
-  j->n_ctas = 0;
   if (j->n_ext > 0 && pr->L > 0)
   {
-    j->cfg = pick_cfg(c, B, j->n_ext, pr->lanes_per_instance, pr->concurrent_instances, pr->cta_thread_limit, &j->solo,
-                      &j->batch_ctas);
+    j->cfg = pick_cfg(c, 0, B, j->n_ext, pr->lanes_per_instance, pr->concurrent_instances, pr->cta_thread_limit,
+                      &j->solo, &j->batch_ctas);
     if (!j->cfg)
     {
-      delete j;
+      destroy_job(c, j);
       return fail(RAMCU_ERR_CAPACITY,
                   "no band tiling for bandwidth %d with %d instances fits this device "
                   "(lanes_per_instance=%d)", B, (int) inst.size(), pr->lanes_per_instance);
     }
     j->n_ctas = j->solo.n_ctas;
-    const int max_ctas = std::max(j->solo.n_ctas, j->batch_ctas);
+    // a pair layout may use up to as many CTAs as the larger of the two passes needs on its own
+    const int max_ctas = std::max(std::max(j->solo.n_ctas, j->batch_ctas), 1) * 2 + 8;
 
     const int W = 2 * B + 1;
-    CK(cudaMallocAsync(&j->d_inst, inst.size() * sizeof(InstDev), c->stream));
-    CK(cudaMemcpyAsync(j->d_inst, inst.data(), inst.size() * sizeof(InstDev),
-                       cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMallocAsync(&j->d_master, std::max(pr->L, 1), c->stream));
-    CK(cudaMallocAsync(&j->d_thigh, inst.size() * sizeof(int), c->stream));
-    CK(cudaMallocAsync(&j->d_tpos, inst.size() * sizeof(int), c->stream));
-    CK(cudaMallocAsync(&j->d_result, 8 * sizeof(int), c->stream));
-    CK(cudaMallocAsync(&j->d_slots, std::max(slots_bytes(j->solo.n_ctas, pr->L), slots_bytes(j->batch_ctas, pr->L)), c->stream));
-    CK(cudaMallocAsync(&j->d_fam, sizeof(FamDev), c->stream));
-    CK(cudaMallocAsync(&j->d_cta_fam, max_ctas * sizeof(int), c->stream));
-    CK(cudaMemsetAsync(j->d_cta_fam, 0, max_ctas * sizeof(int), c->stream));
+    const size_t ob = out_bytes(j->n_ext, pr->L);
+    CKJ(cudaMallocAsync(&j->d_inst, inst.size() * sizeof(InstDev), c->stream));
+    CKJ(cudaMemcpyAsync(j->d_inst, inst.data(), inst.size() * sizeof(InstDev), cudaMemcpyHostToDevice, c->stream));
+    CKJ(cudaMallocAsync(&j->d_out, ob, c->stream));
+    j->h_out = (unsigned char *) pinned_get(c, ob, &j->h_out_cap);
+    if (!j->h_out)
+    {
+      destroy_job(c, j);
+      return fail(RAMCU_ERR_CUDA, "ramcu_job_create: cudaHostAlloc of %zu bytes failed", ob);
+    }
+    CKJ(cudaMallocAsync(&j->d_slots, slots_bytes(pr->L), c->stream));
+    CKJ(cudaMallocAsync(&j->d_fam, 2 * sizeof(FamDev), c->stream));
+    CKJ(cudaMallocAsync(&j->d_cta_fam, max_ctas * sizeof(int), c->stream));
+    CKJ(cudaMemsetAsync(j->d_cta_fam, 0, max_ctas * sizeof(int), c->stream));
+    j->max_ctas = max_ctas;
     if (dbg_rows < 0)   // -outmat mode: path states of -dbg_rows rows, no forced consensus
     {
       const size_t rows = (size_t) -dbg_rows;
-      CK(cudaMallocAsync(&j->d_dbg_path, rows * j->n_ext * W, c->stream));
-      CK(cudaMemsetAsync(j->d_dbg_path, 0, rows * j->n_ext * W, c->stream));
-      CK(cudaMallocAsync(&j->d_dbg_del, (size_t) j->n_ext * W * sizeof(int), c->stream));
-      CK(cudaMallocAsync(&j->d_dbg_idx, rows * j->n_ext * sizeof(int), c->stream));
-      CK(cudaMemsetAsync(j->d_dbg_idx, 0, rows * j->n_ext * sizeof(int), c->stream));
-      CK(cudaMallocAsync(&j->d_dbg_best, rows * j->n_ext * 4 * sizeof(int), c->stream));
-      CK(cudaMallocAsync(&j->d_dbg_sums, rows * 4 * sizeof(int), c->stream));
+      CKJ(cudaMallocAsync(&j->d_dbg_path, rows * j->n_ext * W, c->stream));
+      CKJ(cudaMemsetAsync(j->d_dbg_path, 0, rows * j->n_ext * W, c->stream));
+      CKJ(cudaMallocAsync(&j->d_dbg_idx, rows * j->n_ext * sizeof(int), c->stream));
+      CKJ(cudaMemsetAsync(j->d_dbg_idx, 0, rows * j->n_ext * sizeof(int), c->stream));
+      CKJ(cudaMallocAsync(&j->d_dbg_best, rows * j->n_ext * 4 * sizeof(int), c->stream));
+      CKJ(cudaMallocAsync(&j->d_dbg_sums, rows * 4 * sizeof(int), c->stream));
     }
     if (dbg_rows > 0)
     {
-      CK(cudaMallocAsync(&j->d_dbg_rows, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int), c->stream));
-      CK(cudaMallocAsync(&j->d_dbg_best, (size_t) dbg_rows * j->n_ext * 4 * sizeof(int), c->stream));
-      CK(cudaMallocAsync(&j->d_dbg_sums, (size_t) dbg_rows * 4 * sizeof(int), c->stream));
-      CK(cudaMemsetAsync(j->d_dbg_rows, 0, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int), c->stream));
+      CKJ(cudaMallocAsync(&j->d_dbg_rows, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int), c->stream));
+      CKJ(cudaMallocAsync(&j->d_dbg_best, (size_t) dbg_rows * j->n_ext * 4 * sizeof(int), c->stream));
+      CKJ(cudaMallocAsync(&j->d_dbg_sums, (size_t) dbg_rows * 4 * sizeof(int), c->stream));
+      CKJ(cudaMemsetAsync(j->d_dbg_rows, 0, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int), c->stream));
       if (forced)
       {
-        CK(cudaMallocAsync(&j->d_forced, dbg_rows, c->stream));
-        CK(cudaMemcpyAsync(j->d_forced, forced, dbg_rows, cudaMemcpyHostToDevice, c->stream));
+        CKJ(cudaMallocAsync(&j->d_forced, dbg_rows, c->stream));
+        CKJ(cudaMemcpyAsync(j->d_forced, forced, dbg_rows, cudaMemcpyHostToDevice, c->stream));
       }
     }
     if (getenv("RAMCU_STATS"))
     {
-      CK(cudaMallocAsync(&j->d_dbg_wait, (size_t) 2 * max_ctas * sizeof(long long), c->stream));
-      CK(cudaMemsetAsync(j->d_dbg_wait, 0, (size_t) 2 * max_ctas * sizeof(long long), c->stream));
+      CKJ(cudaMallocAsync(&j->d_dbg_wait, (size_t) 2 * max_ctas * sizeof(long long), c->stream));
+      CKJ(cudaMemsetAsync(j->d_dbg_wait, 0, (size_t) 2 * max_ctas * sizeof(long long), c->stream));
     }
     FamDev &f = j->fam;
     fill_family(f, sc, pr, j->n_ext, j->n_ctas);
+    int *o = reinterpret_cast<int *>(j->d_out);
     f.dbg_wait = j->d_dbg_wait;
     f.lib2 = lib->d_lib2;
     f.libn = lib->d_libn;
     f.inst = j->d_inst;
-    f.master = j->d_master;
-    f.thigh = j->d_thigh;
-    f.tpos = j->d_tpos;
-    f.result = j->d_result;
+    f.result = o;
+    f.thigh = o + 8;
+    f.tpos = o + 8 + j->n_ext;
+    f.master = reinterpret_cast<unsigned char *>(o + 8 + 2 * (size_t) j->n_ext);
     f.slots = j->d_slots;
     f.forced = j->d_forced;
     f.dbg_rows = j->d_dbg_rows;
     f.dbg_path = j->d_dbg_path;
-    f.dbg_del = j->d_dbg_del;
     f.dbg_idx = j->d_dbg_idx;
     f.dbg_best = j->d_dbg_best;
     f.dbg_sums = j->d_dbg_sums;
-    CK(cudaMemcpyAsync(j->d_fam, &f, sizeof(f), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));  // `inst` and `f` are stack/heap temporaries
+    // pageable source: the copy is staged before the call returns, `f` and `inst` may go away
+    CKJ(cudaMemcpyAsync(j->d_fam, &f, sizeof(f), cudaMemcpyHostToDevice, c->stream));
   }
   *out = j;
   return RAMCU_OK;
@@ -746,14 +847,61 @@ extern "C" int ramcu_job_create(ramcu_ctx *c, ramcu_library *lib, int direction,
   return job_create_impl(c, lib, direction, n_cores, cores, sc, pr, 0, nullptr, out);
 }
 
-static int launch_single(ramcu_ctx *c, ramcu_job *j)
+static int *next_ticket(ramcu_ctx *c)
 {
-  CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(int), c->stream));
-  if (j->n_ctas > 1)
-    CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->solo.n_ctas, j->pr.L), c->stream));
-  j->cfg->fn<<<j->solo.n_ctas, j->solo.threads, 0, c->stream>>>(j->d_fam, j->d_cta_fam, c->d_ticket);
+  int *t = c->d_ticket + (c->ticket_next++ % kTickets);
+  return t;
+}
+
+// device results -> the job's pinned host block, in stream order behind the launch
+static int enqueue_fetch(ramcu_ctx *c, ramcu_job *j)
+{
+  CK(cudaMemcpyAsync(j->h_out, j->d_out, out_bytes(j->n_ext, j->pr.L), cudaMemcpyDeviceToHost, c->stream));
+  return RAMCU_OK;
+}
+
+// A launch whose grid fits the device at once is launched cooperatively: the runtime then guarantees
+// that every CTA is resident together (or fails the launch), which is what the column exchange of a
+// multi-CTA family needs; it does not use grid.sync().
+static int launch_unit(ramcu_ctx *c, extend_fn fn, int grid, int threads, const FamDev *d_fams, const int *d_map,
+                       bool needs_residency, int ctas_per_sm_limit)
+{
+  int *ticket = next_ticket(c);
+  CK(cudaMemsetAsync(ticket, 0, sizeof(int), c->stream));
+  if (needs_residency && grid <= ctas_per_sm_limit * c->sm_count && c->coop_ok)
+  {
+    void *args[] = {(void *) &d_fams, (void *) &d_map, (void *) &ticket};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *) fn, dim3(grid), dim3(threads), args, 0, c->stream);
+    if (e == cudaSuccess)
+      return RAMCU_OK;
+    (void) cudaGetLastError();
+    if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorNotSupported)
+      return fail(RAMCU_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+  }
+  fn<<<grid, threads, 0, c->stream>>>(d_fams, d_map, ticket);
   CK(cudaGetLastError());
   return RAMCU_OK;
+}
+
+static int launch_single(ramcu_ctx *c, ramcu_job *j)
+{
+  if (j->n_ctas > 1)
+    CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->pr.L), c->stream));
+  if (j->fam_dirty)
+  {
+    j->fam.n_ctas = j->solo.n_ctas;
+    j->fam.cta0 = 0;
+    j->fam.mate = -1;
+    CK(cudaMemcpyAsync(j->d_fam, &j->fam, sizeof(FamDev), cudaMemcpyHostToDevice, c->stream));
+    j->fam_dirty = false;
+  }
+  j->ran_cfg = j->cfg;
+  j->stats_ctas = j->solo.n_ctas;
+  int rc = launch_unit(c, j->cfg->fn[0], j->solo.n_ctas, j->solo.threads, j->d_fam, j->d_cta_fam, j->solo.n_ctas > 1,
+                       ctas_per_sm(j->cfg, 0, j->solo.threads));
+  if (rc)
+    return rc;
+  return enqueue_fetch(c, j);
 }
 
 extern "C" int ramcu_job_run(ramcu_ctx *c, ramcu_job *j)
@@ -762,7 +910,7 @@ extern "C" int ramcu_job_run(ramcu_ctx *c, ramcu_job *j)
     return fail(RAMCU_ERR_ARG, "ramcu_job_run: NULL argument");
   CK(cudaSetDevice(c->device));
   j->ran = true;
-  j->timed = false;
+  j->timed_gen = 0;
   if (j->n_ctas == 0)
     return RAMCU_OK;
   CK(cudaEventRecord(c->ev0, c->stream));
@@ -770,7 +918,7 @@ extern "C" int ramcu_job_run(ramcu_ctx *c, ramcu_job *j)
   if (rc)
     return rc;
   CK(cudaEventRecord(c->ev1, c->stream));
-  j->timed = true;
+  j->timed_gen = ++c->launch_gen;
   return RAMCU_OK;
 }
 
@@ -810,52 +958,53 @@ extern "C" int ramcu_job_fetch(ramcu_ctx *c, ramcu_job *j, uint8_t *master_out, 
     res->hit_limit = (stop_row >= 0 && stop_row == L - 1) ? 1 : 0;
     return RAMCU_OK;
   }
-  CK(cudaStreamSynchronize(c->stream));
-  int r4[8];
-  CK(cudaMemcpy(r4, j->d_result, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess)
+      return fail(RAMCU_ERR_CUDA, "extension kernel failed: %s%s", cudaGetErrorString(e),
+                  e == cudaErrorLaunchFailure ? " (a column exchange that waited too long traps: is another "
+                                                "process or kernel holding SMs of this device?)" : "");
+  }
+  const int *r4 = reinterpret_cast<const int *>(j->h_out);
+  const int *th = r4 + 8, *tp = r4 + 8 + j->n_ext;
+  const unsigned char *hm = reinterpret_cast<const unsigned char *>(r4 + 8 + 2 * (size_t) j->n_ext);
   res->extended_bp = r4[0] + 1;
   res->rows_processed = r4[1];
   res->stop_row = r4[2];
   res->max_score = r4[3];
   res->hit_limit = (r4[2] >= 0 && r4[2] == j->pr.L - 1) ? 1 : 0;
-  res->lanes_per_instance = j->cfg->G;
-  if (j->timed)
+  res->lanes_per_instance = j->ran_cfg ? j->ran_cfg->G : j->cfg->G;
+  if (j->timed_gen != 0 && j->timed_gen == c->launch_gen)
   {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
       res->kernel_ms = ms;
   }
-  if (j->d_dbg_wait)
+  if (j->d_dbg_wait && j->stats_ctas > 0)
   {
-    const int n_stat = std::max(j->solo.n_ctas, j->batch_ctas);
+    const int n_stat = j->stats_ctas;
     std::vector<long long> w((size_t) 2 * n_stat);
     CK(cudaMemcpy(w.data(), j->d_dbg_wait, w.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    CK(cudaMemset(j->d_dbg_wait, 0, w.size() * sizeof(long long)));
     long long wmin = 1LL << 62, wmax = 0, wsum = 0, tmax = 0;
     int n_seen = 0;
     for (int i = 0; i < n_stat; ++i)
     {
       if (w[2 * i + 1] == 0)
-        continue;   // CTA index not used by the layout that ran
+        continue;
       ++n_seen;
       wmin = std::min(wmin, w[2 * i]);
       wmax = std::max(wmax, w[2 * i]);
       wsum += w[2 * i];
       tmax = std::max(tmax, w[2 * i + 1]);
     }
-    fprintf(stderr, "[ramcu stats] ctas=%d rows=%d cycles/row: total %.0f, exchange wait min %.0f avg %.0f max %.0f\n",
+    fprintf(stderr, "[ramcu stats] ctas=%d rows=%d cycles/row: total %.0f, warp 0 waiting for the column sums: min %.0f avg %.0f max %.0f\n",
             n_seen, r4[1], (double) tmax / std::max(r4[1], 1), (double) wmin / std::max(r4[1], 1),
             (double) wsum / std::max(n_seen, 1) / std::max(r4[1], 1), (double) wmax / std::max(r4[1], 1));
   }
   if (master_out && r4[1] > 0)
-    CK(cudaMemcpy(master_out, j->d_master, r4[1], cudaMemcpyDeviceToHost));
+    memcpy(master_out, hm, r4[1]);
   if (ext_len_out || score_add_out)
-  {
-    std::vector<int> th(j->n_ext), tp(j->n_ext);
-    CK(cudaMemcpy(th.data(), j->d_thigh, j->n_ext * sizeof(int), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(tp.data(), j->d_tpos, j->n_ext * sizeof(int), cudaMemcpyDeviceToHost));
-    map_results(j->n_cores, j->orig, th.data(), tp.data(), ext_len_out, score_add_out);
-  }
+    map_results(j->n_cores, j->orig, th, tp, ext_len_out, score_add_out);
   return RAMCU_OK;
 }
 
@@ -865,8 +1014,7 @@ extern "C" int ramcu_job_free(ramcu_ctx *c, ramcu_job *j)
     return RAMCU_OK;
   if (c)
     cudaSetDevice(c->device);
-  free_job_device(c, j);
-  delete j;
+  destroy_job(c, j);
   return RAMCU_OK;
 }
 
@@ -889,74 +1037,163 @@ extern "C" int ramcu_extend(ramcu_ctx *c, ramcu_library *lib, int direction, int
 // ------------------------------------------------------------------------------------------
 // batches: many independent families sharing the device
 // ------------------------------------------------------------------------------------------
+// A launch unit is a job on its own (one pass per CTA) or the two linked jobs of
+// ramcu_job_create_pair when both are in the list (both passes in the same threads). Units are
+// grouped by kernel instantiation, one launch per group, longest first: CTAs take logical ids from
+// a ticket in start order, so the CTAs of a multi-CTA unit are resident together or ahead of every
+// CTA that could wait for them, and the SMs freed by finished units are back-filled by the next
+// ones of the group. Groups run one after the other on the context's stream: two launches that each
+// hold a partly resident multi-CTA family could wait for each other forever.
+struct Unit
+{
+  ramcu_job *a, *b;   // b != NULL: two passes per CTA
+  const KernelCfg *cfg;
+  int np, n_ctas;
+  long long work;
+};
+
 extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
 {
   if (!c || (n_jobs > 0 && !jobs))
     return fail(RAMCU_ERR_ARG, "ramcu_batch_run: NULL argument");
   CK(cudaSetDevice(c->device));
-  // group by kernel instantiation; one launch per group, families ordered by decreasing work
-  std::vector<int> order;
+  std::vector<Unit> units;
+  std::vector<ramcu_job *> alone;   // too large to share a launch
   for (int i = 0; i < n_jobs; ++i)
   {
     if (!jobs[i])
       return fail(RAMCU_ERR_ARG, "ramcu_batch_run: jobs[%d] == NULL", i);
     jobs[i]->ran = true;
-    jobs[i]->timed = false;
-    if (jobs[i]->n_ctas > 0 && jobs[i]->batch_ctas > 0)
-      order.push_back(i);
+    jobs[i]->timed_gen = 0;
+    jobs[i]->in_batch = true;
   }
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-    if (jobs[a]->cfg != jobs[b]->cfg)
-      return jobs[a]->cfg < jobs[b]->cfg;
-    const long long wa = (long long) jobs[a]->n_ext * jobs[a]->pr.L;
-    const long long wb = (long long) jobs[b]->n_ext * jobs[b]->pr.L;
-    return wa > wb;
+  for (int i = 0; i < n_jobs; ++i)
+  {
+    ramcu_job *j = jobs[i];
+    if (j->n_ctas == 0 || !j->in_batch)
+      continue;
+    ramcu_job *m = j->mate;
+    if (m && m->in_batch && m->n_ctas > 0 && j->pair_cfg && j->pair_batch_ctas > 0)
+    {
+      ramcu_job *a = j->direction ? j : m, *b = j->direction ? m : j;
+      units.push_back(Unit{a, b, j->pair_cfg, 1, j->pair_batch_ctas,
+                           (long long) (a->n_ext + b->n_ext) * j->pr.L});
+      j->in_batch = m->in_batch = false;
+      continue;
+    }
+    if (m && m->in_batch && m->n_ctas > 0 && j->pair_cfg && j->pair_batch_ctas == 0 && j->pair_solo.n_ctas > 0)
+    {
+      // the pair does not fit next to others: launched on its own below, still two passes per CTA
+      ramcu_job *a = j->direction ? j : m, *b = j->direction ? m : j;
+      units.push_back(Unit{a, b, j->pair_cfg, 1, -j->pair_solo.n_ctas, (long long) (a->n_ext + b->n_ext) * j->pr.L});
+      j->in_batch = m->in_batch = false;
+      continue;
+    }
+    if (j->batch_ctas > 0)
+      units.push_back(Unit{j, nullptr, j->cfg, 0, j->batch_ctas, (long long) j->n_ext * j->pr.L});
+    else
+      alone.push_back(j);
+    j->in_batch = false;
+  }
+  if (units.size() == 1 && alone.empty())
+  {
+    // nothing shares the device with this unit: lay it out as a launch of its own
+    if (units[0].np == 0)
+    {
+      alone.push_back(units[0].a);
+      units.clear();
+    }
+    else
+      units[0].n_ctas = -units[0].a->pair_solo.n_ctas;
+  }
+  std::stable_sort(units.begin(), units.end(), [](const Unit &x, const Unit &y) {
+    if ((x.n_ctas < 0) != (y.n_ctas < 0))
+      return x.n_ctas < 0;
+    if (x.cfg != y.cfg)
+      return x.cfg < y.cfg;
+    if (x.np != y.np)
+      return x.np > y.np;
+    return x.work > y.work;
   });
   CK(cudaEventRecord(c->ev0, c->stream));
-  for (int i = 0; i < n_jobs; ++i)
-    if (jobs[i]->n_ctas > 0 && jobs[i]->batch_ctas == 0)
-    {
-      int rc = launch_single(c, jobs[i]);
-      if (rc)
-        return rc;
-    }
+  for (ramcu_job *j : alone)
+  {
+    int rc = launch_single(c, j);
+    if (rc)
+      return rc;
+  }
   size_t p = 0;
-  while (p < order.size())
+  while (p < units.size())
   {
     size_t q = p;
-    const KernelCfg *cfg = jobs[order[p]]->cfg;
+    const KernelCfg *cfg = units[p].cfg;
+    const int np = units[p].np;
+    const bool solo = units[p].n_ctas < 0;
     std::vector<FamDev> fams;
     std::vector<int> cta_fam;
-    while (q < order.size() && jobs[order[q]]->cfg == cfg)
+    bool multi = false;
+    int threads = solo ? units[p].a->pair_solo.threads : batch_threads(cfg, np);
+    while (q < units.size() && units[q].cfg == cfg && units[q].np == np && (units[q].n_ctas < 0) == solo)
     {
-      ramcu_job *j = jobs[order[q]];
-      FamDev f = j->fam;
+      const Unit &u = units[q];
+      const int n_ctas = std::abs(u.n_ctas);
+      FamDev f = u.a->fam;
       f.cta0 = (int) cta_fam.size();
-      f.n_ctas = j->batch_ctas;
-      for (int k = 0; k < j->batch_ctas; ++k)
+      f.n_ctas = n_ctas;
+      f.mate = u.b ? (int) fams.size() + 1 : -1;
+      for (int k = 0; k < n_ctas; ++k)
         cta_fam.push_back((int) fams.size());
       fams.push_back(f);
-      if (j->batch_ctas > 1)
-        CK(cudaMemsetAsync(j->d_slots, 0, slots_bytes(j->batch_ctas, j->pr.L), c->stream));
+      u.a->ran_cfg = cfg;
+      u.a->stats_ctas = std::min(n_ctas, u.a->max_ctas);
+      if (u.b)
+      {
+        FamDev g = u.b->fam;
+        g.cta0 = f.cta0;
+        g.n_ctas = n_ctas;
+        g.mate = -1;
+        fams.push_back(g);
+        u.b->ran_cfg = cfg;
+        u.b->stats_ctas = 0;
+      }
+      if (n_ctas > 1)
+      {
+        multi = true;
+        CK(cudaMemsetAsync(u.a->d_slots, 0, slots_bytes(u.a->pr.L), c->stream));
+        if (u.b)
+          CK(cudaMemsetAsync(u.b->d_slots, 0, slots_bytes(u.b->pr.L), c->stream));
+      }
+      u.a->fam_dirty = true;
       ++q;
+      if (solo)
+        break;   // one unit per launch
     }
     FamDev *d_fams = nullptr;
     int *d_map = nullptr;
     CK(cudaMallocAsync(&d_fams, fams.size() * sizeof(FamDev), c->stream));
     CK(cudaMallocAsync(&d_map, cta_fam.size() * sizeof(int), c->stream));
+    // pageable sources: the copies are staged before the calls return, so the vectors may go away
     CK(cudaMemcpyAsync(d_fams, fams.data(), fams.size() * sizeof(FamDev), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_map, cta_fam.data(), cta_fam.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(int), c->stream));
-    // pageable sources: the copies above have completed on return, so the vectors may go away
-    cfg->fn<<<(int) cta_fam.size(), kBatchThreads, 0, c->stream>>>(d_fams, d_map, c->d_ticket);
-    CK(cudaGetLastError());
+    int rc = launch_unit(c, cfg->fn[np], (int) cta_fam.size(), threads, d_fams, d_map, multi, ctas_per_sm(cfg, np, threads));
+    if (rc)
+      return rc;
     CK(cudaFreeAsync(d_fams, c->stream));
     CK(cudaFreeAsync(d_map, c->stream));
     p = q;
   }
   CK(cudaEventRecord(c->ev1, c->stream));
+  ++c->launch_gen;
   for (int i = 0; i < n_jobs; ++i)
-    jobs[i]->timed = true;
+  {
+    jobs[i]->timed_gen = c->launch_gen;
+    if (jobs[i]->n_ctas > 0)
+    {
+      int rc = enqueue_fetch(c, jobs[i]);
+      if (rc)
+        return rc;
+    }
+  }
   return RAMCU_OK;
 }
 
@@ -967,8 +1204,9 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
 // (ram_extend.c:445-499), then extends left with those bounds. When that step leaves every bound
 // as it was (the caller checks: ramx_boundary.c compares the bounds it is handed for the left
 // pass with the ones used here), the two passes are independent column loops over the same
-// cores. Running them as two families of one launch puts CTAs of both on every SM, so one pass
-// computes while the other waits for its per-column grid exchange.
+// cores. Every thread then carries an instance band of BOTH passes and the passes take turns row by
+// row: while the column sums of one pass travel between the CTAs, the other pass's row is computed
+// (DESIGN.md 3.4).
 extern "C" int ramcu_job_create_pair(ramcu_ctx *c, ramcu_library *lib, int n_cores,
                                      const ramcu_core_t *cores, const ramcu_scoring_t *sc,
                                      const ramcu_params_t *pr, ramcu_job **right, ramcu_job **left)
@@ -976,81 +1214,33 @@ extern "C" int ramcu_job_create_pair(ramcu_ctx *c, ramcu_library *lib, int n_cor
   if (!c || !pr || !right || !left || (n_cores > 0 && !cores))
     return fail(RAMCU_ERR_ARG, "ramcu_job_create_pair: NULL argument");
   *right = *left = nullptr;
-  int n_r = 0, n_l = 0;
-  for (int i = 0; i < n_cores; ++i)
-  {
-    n_r += cores[i].right_extendable ? 1 : 0;
-    n_l += cores[i].left_extendable ? 1 : 0;
-  }
-  ramcu_params_t p = *pr;
-  bool together = false;
-  if (n_r > 0 && n_l > 0 && pr->L > 0 && pr->bandwidth >= 0 && pr->bandwidth <= RAMCU_MAX_BANDWIDTH)
-  {
-    CK(cudaSetDevice(c->device));
-    Plan solo;
-    int nb = 0;
-    const KernelCfg *k0 = pick_cfg(c, pr->bandwidth, std::max(n_r, n_l), pr->lanes_per_instance,
-                                   pr->concurrent_instances, pr->cta_thread_limit, &solo, &nb);
-    if (k0)
-    {
-      // same lanes per instance as the family alone, with full registers if both passes fit the
-      // device side by side, else the tiling compiled for half the registers; failing that, the
-      // cheapest other half-register tiling of this band (by the single-family cost model) that fits
-      auto fits = [&](int G, int maxt, double *cost) -> bool {
-        Plan sr, sl;
-        int br = 0, bl = 0;
-        const KernelCfg *kr = pick_cfg(c, pr->bandwidth, n_r, G, pr->concurrent_instances, maxt, &sr, &br);
-        const KernelCfg *kl = pick_cfg(c, pr->bandwidth, n_l, G, pr->concurrent_instances, maxt, &sl, &bl);
-        if (!kr || kr != kl || kr->maxt != maxt || kr->G != G || br <= 0 || bl <= 0)
-          return false;
-        if ((long long) br + bl > (long long) ctas_per_sm(kr, kBatchThreads) * c->sm_count)
-          return false;
-        if (cost)
-          *cost = solo_cost(c, kr, std::max(n_r, n_l), n_r >= n_l ? sr : sl);
-        return true;
-      };
-      const int tries[2] = {k0->maxt, 512};
-      for (int t = 0; t < 2 && !together; ++t)
-      {
-        if (pr->cta_thread_limit > 0 && tries[t] != pr->cta_thread_limit)
-          continue;
-        if (!fits(k0->G, tries[t], nullptr))
-          continue;
-        p.lanes_per_instance = k0->G;
-        p.cta_thread_limit = tries[t];
-        together = true;
-      }
-      if (!together && pr->lanes_per_instance <= 0 && (pr->cta_thread_limit <= 0 || pr->cta_thread_limit == 512))
-      {
-        double best_cost = 0;
-        for (int G = 1; G <= 32; ++G)
-        {
-          double cost = 0;
-          if (G == k0->G || !fits(G, 512, &cost))
-            continue;
-          if (!together || cost < best_cost)
-          {
-            best_cost = cost;
-            p.lanes_per_instance = G;
-            p.cta_thread_limit = 512;
-            together = true;
-          }
-        }
-      }
-    }
-  }
-  int rc = job_create_impl(c, lib, 1, n_cores, cores, sc, &p, 0, nullptr, right);
+  int rc = job_create_impl(c, lib, 1, n_cores, cores, sc, pr, 0, nullptr, right);
   if (!rc)
-    rc = job_create_impl(c, lib, 0, n_cores, cores, sc, &p, 0, nullptr, left);
+    rc = job_create_impl(c, lib, 0, n_cores, cores, sc, pr, 0, nullptr, left);
   if (rc)
   {
     ramcu_job_free(c, *right);
     *right = nullptr;
     return rc;
   }
-  if (!together)   // ramcu_batch_run then launches each pass on its own, one after the other
-    (*right)->batch_ctas = (*left)->batch_ctas = 0;
-
+  ramcu_job *a = *right, *b = *left;
+  if (a->n_ctas > 0 && b->n_ctas > 0)
+  {
+    Plan solo;
+    int nb = 0;
+    const KernelCfg *k = pick_cfg(c, 1, pr->bandwidth, std::max(a->n_ext, b->n_ext), pr->lanes_per_instance,
+                                  pr->concurrent_instances, pr->cta_thread_limit, &solo, &nb);
+    if (k && solo.n_ctas <= std::min(a->max_ctas, b->max_ctas))
+    {
+      if (nb > std::min(a->max_ctas, b->max_ctas))
+        nb = 0;
+      a->mate = b;
+      b->mate = a;
+      a->pair_cfg = b->pair_cfg = k;
+      a->pair_solo = b->pair_solo = solo;
+      a->pair_batch_ctas = b->pair_batch_ctas = nb;
+    }
+  }
   return RAMCU_OK;
 }
 
@@ -1113,7 +1303,7 @@ extern "C" int ramcu_extend_paths(ramcu_ctx *c, ramcu_library *lib, int directio
     CK(cudaMemcpy(path.data(), j->d_dbg_path, path.size(), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(best.data(), j->d_dbg_best, best.size() * sizeof(int), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(idx.data(), j->d_dbg_idx, idx.size() * sizeof(int), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(cons.data(), j->d_master, rows, cudaMemcpyDeviceToHost));
+    memcpy(cons.data(), j->h_out + (8 + 2 * (size_t) j->n_ext) * sizeof(int), rows);
     for (size_t r = 0; r < rows; ++r)
       for (size_t e = 0; e < ne; ++e)
       {

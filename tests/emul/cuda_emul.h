@@ -115,6 +115,11 @@ static inline unsigned __brev(unsigned x)
   x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
   return __builtin_bswap32(x);
 }
+static inline void __threadfence_block() { __sync_synchronize(); }
+static inline void __syncwarp()
+{
+  pthread_barrier_wait(&emul_warp->bar);
+}
 static inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __sync_fetch_and_add(p, v); }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __sync_fetch_and_or(p, v); }

@@ -92,8 +92,8 @@ static int launch(LaunchArgs proto, int grid, int block)
   return 0;
 }
 
-struct Cfg { int C, G, WS; extend_fn fn; };
-#define ECFG(C_, G_, WS_) {C_, G_, WS_, extend_kernel<C_, G_, WS_, 1024>}
+struct Cfg { int C, G, WS; extend_fn fn, fn2; };
+#define ECFG(C_, G_, WS_) {C_, G_, WS_, extend_kernel<C_, G_, WS_, 1024, 1>, extend_kernel<C_, G_, WS_, 1024, 2>}
 static const Cfg kCfgs[] = {
   ECFG(11, 1, 11), ECFG(6, 2, 11), ECFG(3, 4, 11), ECFG(4, 3, 11),      // B = 5, static band
   ECFG(29, 1, 29), ECFG(15, 2, 29), ECFG(8, 4, 29), ECFG(4, 8, 29),     // B = 14
@@ -159,7 +159,7 @@ static int emul_extend_impl(int C, int G, int WS, int threads, const uint8_t *se
   for (int i = 0; i < n_ext; ++i)
     orig[i] = inst[i].orig;
   std::vector<unsigned char> master(p2.L + 1);
-  std::vector<unsigned long long> slots(std::max((size_t) 2 * n_ctas * 4, (size_t) (p2.L + 1) * 4 * kRedStride), 0);
+  std::vector<unsigned long long> slots((size_t) (p2.L + 1) * 4 * kRedStride, 0);
   std::vector<int> drows, dbest, dsums;
   FamDev f;
   fill_family(f, sc, &p2, n_ext, n_ctas);
@@ -182,16 +182,14 @@ static int emul_extend_impl(int C, int G, int WS, int threads, const uint8_t *se
     f.forced = forced;
   }
   std::vector<unsigned char> dpath;
-  std::vector<int> ddel, didx;
+  std::vector<int> didx;
   if (path_out)   // -outmat mode (ramcu_extend_paths)
   {
     dpath.assign((size_t) p2.L * n_ext * W, 0);
-    ddel.assign((size_t) n_ext * W, 0);
     didx.assign((size_t) p2.L * n_ext, 0);
     dbest.assign((size_t) p2.L * n_ext * 4, 0);
     dsums.assign((size_t) p2.L * 4, 0);
     f.dbg_path = dpath.data();
-    f.dbg_del = ddel.data();
     f.dbg_idx = didx.data();
     f.dbg_best = dbest.data();
     f.dbg_sums = dsums.data();
@@ -280,7 +278,7 @@ extern "C" int emul_twobit(const uint8_t *blob, unsigned long long blob_bytes, c
   unsigned int nslow = 0;
   {
     const std::function<void()> k = [&]() {
-      twobit_windows_kernel(ab, blob_bytes, win, n_windows, total, lib2_out, n_chunks, slow.data(), &nslow);
+      twobit_windows_kernel(ab, blob_bytes, win, n_windows, total, lib2_out, n_chunks, slow.data(), &nslow, (unsigned) slow.size());
     };
     LaunchArgs a = {};
     a.gen = &k;
@@ -289,7 +287,7 @@ extern "C" int emul_twobit(const uint8_t *blob, unsigned long long blob_bytes, c
   }
   {
     const std::function<void()> k = [&]() {
-      twobit_boundary_kernel(ab, blob_bytes, win, n_windows, total, lib2_out, n_chunks, slow.data(), &nslow);
+      twobit_boundary_kernel(ab, blob_bytes, win, n_windows, total, lib2_out, n_chunks, slow.data(), &nslow, (unsigned) slow.size());
     };
     LaunchArgs a = {};
     a.gen = &k;
@@ -297,4 +295,98 @@ extern "C" int emul_twobit(const uint8_t *blob, unsigned long long blob_bytes, c
       return -1;
   }
   return (int) nslow;
+}
+
+// Same contract as ramcu_extend_pair() (include/ramcu.h): both passes of a family in the same threads
+// (extend_kernel<..., NP = 2>), the right pass as launch unit, the left pass as its mate.
+extern "C" int emul_extend_pair(int C, int G, int WS, int threads, const uint8_t *seq, uint64_t seq_len,
+                                int n_cores, const ramcu_core_t *cores, const ramcu_scoring_t *sc,
+                                const ramcu_params_t *pr, uint8_t *master_r, int32_t *ext_len_r,
+                                int32_t *score_add_r, ramcu_result_t *res_r, uint8_t *master_l,
+                                int32_t *ext_len_l, int32_t *score_add_l, ramcu_result_t *res_l)
+{
+  const Cfg *cfg = nullptr;
+  for (const Cfg &c : kCfgs)
+    if (c.C == C && c.G == G && c.WS == WS)
+      cfg = &c;
+  const int W = 2 * pr->bandwidth + 1;
+  if (!cfg || (WS && WS != W) || C * G < W || threads % 32 || threads > 1024)
+    return -2;
+  const unsigned long long n_chunks = (seq_len + 31) / 32;
+  std::vector<uint32_t> a2(n_chunks * 2 + 8, 0), an(n_chunks + 8, 0xffffffffu);
+  {
+    LaunchArgs p = {};
+    p.pfn = pack_library_kernel;
+    p.bytes = seq;
+    p.len = seq_len;
+    p.n_chunks = n_chunks;
+    p.lib2 = a2.data() + 4;
+    p.libn = an.data() + 4;
+    if (launch(p, 2, 32))
+      return -1;
+  }
+  std::vector<InstDev> inst[2];
+  std::vector<int> orig[2], thigh[2], tpos[2], result[2];
+  std::vector<unsigned char> master[2];
+  std::vector<unsigned long long> slots[2];
+  FamDev f[2];
+  int n_ext_max = 0;
+  for (int p = 0; p < 2; ++p)
+  {
+    flatten_cores(p == 0 ? 1 : 0, n_cores, cores, seq_len, inst[p]);
+    n_ext_max = std::max(n_ext_max, (int) inst[p].size());
+    if (inst[p].empty() || pr->L <= 0)
+      return -3;
+  }
+  const int per_cta_max = std::max(1, (threads / 32) * inst_per_warp(G));
+  const int n_ctas = (n_ext_max + per_cta_max - 1) / per_cta_max;
+  threads = cta_threads(n_ext_max, n_ctas, G);
+  for (int p = 0; p < 2; ++p)
+  {
+    const int n_ext = (int) inst[p].size();
+    orig[p].resize(n_ext);
+    for (int i = 0; i < n_ext; ++i)
+      orig[p][i] = inst[p][i].orig;
+    thigh[p].assign(n_ext, 0);
+    tpos[p].assign(n_ext, 0);
+    result[p].assign(8, 0);
+    master[p].assign(pr->L + 1, 0);
+    slots[p].assign((size_t) (pr->L + 1) * 4 * kRedStride, 0);
+    fill_family(f[p], sc, pr, n_ext, n_ctas);
+    f[p].lib2 = a2.data() + 4;
+    f[p].libn = an.data() + 4;
+    f[p].inst = inst[p].data();
+    f[p].master = master[p].data();
+    f[p].thigh = thigh[p].data();
+    f[p].tpos = tpos[p].data();
+    f[p].result = result[p].data();
+    f[p].slots = slots[p].data();
+  }
+  f[0].mate = 1;
+  std::vector<int> cta_fam(n_ctas, 0);
+  int ticket = 0;
+  LaunchArgs a = {};
+  a.fn = cfg->fn2;
+  a.fams = f;
+  a.cta_fam = cta_fam.data();
+  a.ticket = &ticket;
+  if (launch(a, n_ctas, threads))
+    return -1;
+  uint8_t *mo[2] = {master_r, master_l};
+  int32_t *eo[2] = {ext_len_r, ext_len_l}, *so[2] = {score_add_r, score_add_l};
+  ramcu_result_t *ro[2] = {res_r, res_l};
+  for (int p = 0; p < 2; ++p)
+  {
+    memset(ro[p], 0, sizeof(ramcu_result_t));
+    ro[p]->n_extendable = (int) inst[p].size();
+    ro[p]->extended_bp = result[p][0] + 1;
+    ro[p]->rows_processed = result[p][1];
+    ro[p]->stop_row = result[p][2];
+    ro[p]->max_score = result[p][3];
+    ro[p]->hit_limit = (result[p][2] >= 0 && result[p][2] == pr->L - 1) ? 1 : 0;
+    ro[p]->lanes_per_instance = G;
+    memcpy(mo[p], master[p].data(), result[p][1]);
+    map_results(n_cores, orig[p], thigh[p].data(), tpos[p].data(), eo[p], so[p]);
+  }
+  return 0;
 }

@@ -189,6 +189,8 @@ class Emulator:
         lib.emul_extend.argtypes = [i32, i32, i32, i32, vp, u64, i32, i32, vp, P(Scoring), P(Params),
                                     vp, vp, vp, P(ExtendResult), i32, vp, vp, vp, vp]
         lib.emul_cfg.argtypes = [i32, P(i32), P(i32), P(i32)]
+        lib.emul_extend_pair.argtypes = [i32, i32, i32, i32, vp, u64, i32, vp, P(Scoring), P(Params),
+                                         vp, vp, vp, P(ExtendResult), vp, vp, vp, P(ExtendResult)]
         lib.emul_extend_paths.argtypes = [i32, i32, i32, i32, vp, u64, i32, i32, vp, P(Scoring), P(Params),
                                           vp, vp, vp, P(ExtendResult), vp, vp, vp]
 
@@ -232,6 +234,28 @@ class Emulator:
                     stop_row=res.stop_row, hit_limit=res.hit_limit, max_score=res.max_score,
                     n_extendable=res.n_extendable, master=master[: res.rows_processed].copy(),
                     ext_len=ext_len, score_add=score_add, rows=rows, best=best, sums=sums)
+
+
+def emul_extend_pair(emul, cfg, cores, seq, sc, p, threads=128):
+    """ramcu_extend_pair through the CPU emulation: both passes in the same threads (NP = 2)"""
+    cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    n = cores.size
+    outs = []
+    bufs = []
+    for _ in range(2):
+        bufs.append((np.zeros(max(p.L, 1) + 1, dtype=np.uint8), np.zeros(n, dtype=np.int32),
+                     np.zeros(n, dtype=np.int32), ExtendResult()))
+    rc = emul.lib.emul_extend_pair(cfg[0], cfg[1], cfg[2], threads, seq.ctypes.data, seq.size, n, cores.ctypes.data,
+                                   C.byref(sc), C.byref(p), bufs[0][0].ctypes.data, bufs[0][1].ctypes.data,
+                                   bufs[0][2].ctypes.data, C.byref(bufs[0][3]), bufs[1][0].ctypes.data,
+                                   bufs[1][1].ctypes.data, bufs[1][2].ctypes.data, C.byref(bufs[1][3]))
+    assert rc == 0, f"emul_extend_pair rc={rc}"
+    for master, ext_len, score_add, res in bufs:
+        outs.append(dict(extended_bp=res.extended_bp, rows_processed=res.rows_processed, stop_row=res.stop_row,
+                         hit_limit=res.hit_limit, max_score=res.max_score, n_extendable=res.n_extendable,
+                         master=master[: res.rows_processed].copy(), ext_len=ext_len, score_add=score_add))
+    return outs   # [right, left]
 
 
 def emul_extend_paths(emul, cfg, direction, cores, seq, sc, p, threads=128):

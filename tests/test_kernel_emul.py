@@ -172,3 +172,18 @@ def test_emul_positive_gap_penalties(emul, oracle, cfg, gaps):
         want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
         got = emul.extend(cfg, d, fam.cores, fam.sequence, osc.to_product(), p, threads=64)
         support.compare_extend(want, got, f"cfg={cfg} gaps={gaps} dir={d}")
+
+
+@pytest.mark.parametrize("cfg,B,threads,n", [((10, 3, 29), 14, 64, 23), ((8, 4, 29), 14, 32, 9), ((29, 1, 29), 14, 64, 70),
+                                           ((27, 3, 81), 40, 32, 12), ((16, 4, 0), 20, 64, 17)])
+def test_emul_two_passes_in_the_same_threads(emul, oracle, cfg, B, threads, n):
+    """extend_kernel<..., NP = 2>: the right and the left pass of a family take turns in the same
+    threads (barrier-free column handshake); different numbers of extendable cores per direction,
+    passes that stop at different rows, one CTA and several"""
+    fam = synth.make_family(131 + n, n, 150, 0.15, pad=2 * B, one_sided_frac=0.35, n_frac=0.01)
+    osc = oracle.scoring("14p43g")
+    p = make_params(bandwidth=B, minimprovement=30, L=400, when_to_stop=20)
+    got = support.emul_extend_pair(emul, cfg, fam.cores, fam.sequence, osc.to_product(), p, threads=threads)
+    for d, g in zip((1, 0), got):
+        want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+        support.compare_extend(want, g, f"cfg={cfg} dir={d}")
