@@ -87,48 +87,67 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU baseline: the reference's own extend_alignment() object code (oracle/_ref/libramref.so)
 # ---------------------------------------------------------------------------------------------
+CPU_SAMPLE = dict(n=1000, rows=300)   # instances / columns per direction of the CPU sample (config-4 shape)
+# the reference's extend_alignment() on the WHOLE config-4 family (N=10000, 2 x 5100 columns), one process, in the
+# build container while tests/golden/full_config4.npz was produced (tests/golden/make_golden_full.py)
+FULL_CONFIG4_CPU = {"seconds": 879.0, "gcups": 0.0376, "where": "build container (Xeon, 8 vCPU), one core per direction"}
+
+
 def _cpu_worker(args):
-    seed, n, flank, kind = args
+    seed, n, flank, kind, rows, steps = args
     from repeatafterme_b200 import synth
     from repeatafterme_b200.abi import make_params
     from tests import support
     fam = synth.make_family(seed, n, flank, WORKLOAD["divergence"])
     p = make_params(bandwidth=WORKLOAD["bandwidth"], minimprovement=WORKLOAD["minimprovement"],
-                    cappenalty=WORKLOAD["cappenalty"], L=WORKLOAD["L"], when_to_stop=WORKLOAD["when_to_stop"])
+                    cappenalty=WORKLOAD["cappenalty"], L=min(WORKLOAD["L"], rows), when_to_stop=WORKLOAD["when_to_stop"])
     ora = support.Oracle()
     sc = ora.scoring(WORKLOAD["matrix"])
     ref = support.Reference.try_load() if kind == "reference" else None
-    secs, cu = 0.0, 0.0
-    for d in (1, 0):
-        if ref is not None:
-            o = ref.extend(d, fam.cores, fam.sequence, sc, p)
-            secs += o["seconds"]
-            rows = o["rows_processed"]
-        else:
-            t0 = time.perf_counter()
-            o = ora.extend(d, fam.cores, fam.sequence, sc, p)
-            secs += time.perf_counter() - t0
-            rows = o["rows_processed"]
-        next_ = int(((fam.cores["right_extendable"] if d else fam.cores["left_extendable"]) != 0).sum())
-        cu += rows * next_ * (2 * WORKLOAD["bandwidth"] + 1) * 4.0
-    return secs, cu
+    out = []
+    for _ in range(steps):
+        secs, cu = 0.0, 0.0
+        for d in (1, 0):
+            if ref is not None:
+                o = ref.extend(d, fam.cores, fam.sequence, sc, p)
+                secs += o["seconds"]
+            else:
+                t0 = time.perf_counter()
+                o = ora.extend(d, fam.cores, fam.sequence, sc, p)
+                secs += time.perf_counter() - t0
+            next_ = int(((fam.cores["right_extendable"] if d else fam.cores["left_extendable"]) != 0).sum())
+            cu += o["rows_processed"] * next_ * (2 * WORKLOAD["bandwidth"] + 1) * 4.0
+        out.append((secs, cu))
+    return out
 
 
-def cpu_baseline(n_inst: int, flank: int, procs: int, seed0: int = 900):
-    """one sample family per process on `procs` host cores at once (the reference is single
-    threaded; util/extend-stk.pl runs one RAMExtend process per family). Returns
-    (aggregate GCUPS, single-process GCUPS, kind)."""
+def cpu_baseline(procs: int, steps: int = 1, seed0: int = 900, n_inst: int = CPU_SAMPLE["n"],
+                 rows: int = CPU_SAMPLE["rows"]):
+    """The reference's own extend_alignment() object code (oracle/_ref/libramref.so; the oracle port if
+    the reference could not be built) on `procs` host cores at once, one process per core as
+    util/extend-stk.pl runs one RAMExtend per family: every process extends its own synthetic family
+    of the config-4 shape (n_inst instances x 5 kb flanks, not cache resident) for the first `rows`
+    columns of both directions, `steps` times. Returns per step (aggregate GCUPS = cell updates of all
+    processes / slowest process, single-process GCUPS), the kind and the wall seconds."""
     import multiprocessing as mp
     kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libramref.so")) else "port"
-    ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        outs = pool.map(_cpu_worker, [(seed0 + i, n_inst, flank, kind) for i in range(procs)])
+    with mp.get_context("spawn").Pool(procs) as pool:
+        outs = pool.map(_cpu_worker, [(seed0 + i, n_inst, WORKLOAD["flank"], kind, rows, steps) for i in range(procs)])
     wall = time.perf_counter() - t0
-    cu = sum(o[1] for o in outs)
-    slowest = max(o[0] for o in outs)
-    single = outs[0][1] / outs[0][0] / 1e9
-    return cu / slowest / 1e9, single, kind, wall
+    per_step = []
+    for k in range(steps):
+        cu = sum(o[k][1] for o in outs)
+        slowest = max(o[k][0] for o in outs)
+        per_step.append((cu / slowest / 1e9, outs[0][k][1] / outs[0][k][0] / 1e9, slowest))
+    return per_step, kind, wall
+
+
+def cpu_sample_text(cores: int) -> str:
+    return (f"{cores} processes at once (one per host core, as extend-stk.pl runs one RAMExtend per family), each the "
+            f"two extend_alignment() calls of one synthetic family of {CPU_SAMPLE['n']} instances x {WORKLOAD['flank']} bp "
+            f"flanks (config-4 shape) limited to the first {CPU_SAMPLE['rows']} columns per direction; DP time only "
+            f"(clock_gettime around the calls); aggregate = cell updates of all processes / slowest process")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -137,23 +156,18 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_inst, flank = 32, WORKLOAD["flank"]
-    vals = []
-    for step in range(args.warmup + args.steps):
-        agg, single, kind, wall = cpu_baseline(n_inst, flank, cores, seed0=900 + 1000 * step)
-        if step >= args.warmup:
-            vals.append((agg, single, wall))
+    per_step, kind, wall = cpu_baseline(cores, steps=args.warmup + args.steps)
+    vals = per_step[args.warmup:]
     agg = float(np.mean([v[0] for v in vals]))
     single = float(np.mean([v[1] for v in vals]))
-    sample = (f"{cores} processes, each the two extend_alignment() calls of one synthetic family of "
-              f"{n_inst} instances x {flank} bp flanks (config-4 shape, DP time only via clock_gettime)")
     line = {"impl": "reference", "metric": "banded_dp_gcups", "value": round(agg, 4), "unit": "GCUPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * float(np.mean([v[2] for v in vals])), 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config(args.gpus),
             "cpu_baseline": {"value": round(agg, 4), "unit": "GCUPS", "cores": cores, "kind": kind,
-                             "sample": sample, "single_process_value": round(single, 4)},
+                             "sample": cpu_sample_text(cores), "single_process_value": round(single, 4),
+                             "full_config4_single_process": FULL_CONFIG4_CPU},
             "e2e": {"value": round(agg, 4), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -162,8 +176,120 @@ def workload_config(n_gpus: int) -> dict:
     return {"workload": "synthetic single family per GPU: 10k instances, ~15% divergence, 5 kb flanks, "
                         "bandwidth 40, 14p43g, minimprovement 30, L 20000 (BASELINE configs[3])",
             "instances": WORKLOAD["n"], "flank_bp": WORKLOAD["flank"], "bandwidth": WORKLOAD["bandwidth"],
-            "matrix": WORKLOAD["matrix"], "families_per_step": n_gpus, "parallelism": f"families x{n_gpus}",
-            "l2": "L2 flushed between timed steps (256 MiB write)"}
+            "matrix": WORKLOAD["matrix"], "minimprovement": WORKLOAD["minimprovement"], "L": WORKLOAD["L"],
+            "families_per_step": n_gpus, "parallelism": f"families x{n_gpus}",
+            "l2": "GPU arm: L2 flushed between timed steps (256 MiB write); CPU arm: working set larger than the caches"}
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[4]: synthetic genome-scale round
+# ---------------------------------------------------------------------------------------------
+def config5_round(args, rc, stream, world, rank, local, barrier, peak_gops):
+    """2 000 seeded families (N 100-10k log-uniform, bandwidth 20-100, flank 0.5-5 kb, 10 % one-sided
+    cores; synth.config5_specs) -- the SAME set at every GPU count, sharded by family over the ranks
+    (longest-processing-time-first on N x band x flank, no communication between ranks: strong
+    scaling). `--families K` (K > 0) takes the first K families of a seeded permutation instead.
+    Per rank: the shard's families are generated as 2-bit packed libraries (4 bases per byte, as a
+    .2bit stores them), then
+      device leg : libraries decoded into HBM and jobs created beforehand; CUDA events around ONE
+                   ramcu_batch_run of all 2 x F column loops (right+left pass of a family in the same
+                   threads where both row states fit); median of the timed runs
+      e2e leg    : host blobs in, host results out: ramcu_library_from_twobit + ramcu_job_create_pair
+                   + ramcu_batch_run + ramcu_job_fetch + frees, wall clock
+    and the families of the full-size parity sample that fall into the shard are compared with the
+    reference's outputs (tests/golden/full_config5_sample.npz)."""
+    import torch
+    from repeatafterme_b200 import batch, synth
+    specs = synth.config5_specs(5, 2000)
+    ids = list(range(len(specs)))
+    if args.families > 0:
+        ids = sorted(np.random.default_rng(0).permutation(len(specs))[: args.families].tolist())
+    costs = [batch.family_cost(specs[i]["n"], specs[i]["params"]["bandwidth"], specs[i]["flank"]) for i in ids]
+    mine = [ids[k] for k in batch.lpt_shard(costs, world)[rank]]
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    procs = max(1, (os.cpu_count() or 1) // max(local_world, 1))
+    t0 = time.perf_counter()
+    fams = synth.generate_packed_families([specs[i] for i in mine], procs=procs)
+    gen_s = time.perf_counter() - t0
+    log(f"[rank {rank}] config 5: {len(fams)} of {len(ids)} families, {sum(f.total for f in fams) / 1e9:.2f} Gbases "
+        f"generated in {gen_s:.0f} s on {procs} processes")
+
+    # ---- device-resident leg --------------------------------------------------------------------------
+    total_inst = sum(f.n for f in fams)
+    libs, jobs, prs = [], [], []
+    for f in fams:
+        pr = dict(f.params)
+        sc = rc.scoring(pr.pop("matrix"))
+        pr["concurrent_instances"] = total_inst - f.n
+        from repeatafterme_b200.abi import make_params
+        prm = make_params(**pr)
+        h = rc.library_from_twobit(f.blob, f.windows, f.n_start, f.n_len, f.total)
+        libs.append(h)
+        prs.append(prm)
+        jobs += list(rc.job_create_pair(h, f.cores, sc, prm))
+    rc.batch_run(jobs)               # warm-up: first use of every tiling loads its code
+    torch.cuda.synchronize()
+    dev = []
+    for _ in range(max(1, args.family_runs)):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rc.batch_run(jobs)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        dev.append(e0.elapsed_time(e1) * 1e-3)
+    cu, outs = 0.0, {}
+    for k, f in enumerate(fams):
+        for d, j in zip((1, 0), jobs[2 * k: 2 * k + 2]):
+            o = rc.job_fetch(j, f.n, prs[k].L)
+            cu += o[0].rows_processed * o[0].n_extendable * (2 * prs[k].bandwidth + 1) * 4.0
+            outs[(mine[k], d)] = o
+    for j in jobs:
+        rc.job_free(j)
+    for h in libs:
+        rc.free_library(h)
+
+    # parity at full size against the reference, for the sample families of this shard
+    checked = 0
+    golden = os.path.join(ROOT, "tests", "golden", "full_config5_sample.npz")
+    if os.path.exists(golden):
+        z = np.load(golden, allow_pickle=False)
+        meta = json.loads(str(z["meta"]))
+        for key, m in meta.items():
+            if int(key) not in mine:
+                continue
+            for d in (1, 0):
+                o, rows = outs[(int(key), d)], m[f"rows{d}"]
+                if not (o[0].extended_bp == m[f"bp{d}"] and o[0].rows_processed == rows and
+                        np.array_equal(o[1][:rows], z[f"{key}_master{d}"][:rows]) and
+                        np.array_equal(o[2], z[f"{key}_ext_len{d}"]) and np.array_equal(o[3], z[f"{key}_score_add{d}"])):
+                    raise SystemExit(f"bench.py: config-5 family {key} direction {d} differs from the reference golden")
+            checked += 1
+    del outs
+
+    # ---- end-to-end leg -----------------------------------------------------------------------------------
+    e2e = []
+    for _ in range(max(1, args.family_runs)):
+        barrier()
+        t0 = time.perf_counter()
+        batch.extend_families(rc, fams)
+        torch.cuda.synchronize()
+        e2e.append(time.perf_counter() - t0)
+    h2d = int(sum(f.blob.nbytes + 2 * f.cores.nbytes for f in fams))
+    stats = (float(np.median(dev)), float(np.median(e2e)), float(len(fams)), float(cu), float(total_inst), gen_s)
+    chk = torch.tensor([float(checked)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+    extra = {"what": "BASELINE configs[4]: %d seeded families (N 100-10k log-uniform, bandwidth 20-100, flank 0.5-5 kb, 10%% "
+                     "one-sided cores), the same set at every GPU count, sharded by family (LPT) over the ranks with no "
+                     "communication; device = CUDA events around one ramcu_batch_run of all column loops with libraries "
+                     "and jobs resident, e2e = 2-bit packed host libraries in / host results out (upload + decode, job "
+                     "creation, run, fetch); per rank the median of %d runs after a warm-up, max over ranks"
+                     % (len(ids), max(1, args.family_runs)),
+             "families_checked_against_reference_golden": int(chk.item()),
+             "h2d_bytes_rank0": h2d}
+    return stats, extra
 
 
 # ---------------------------------------------------------------------------------------------
@@ -248,12 +374,31 @@ def run_cuda(args):
     cu_step = sum(o[0].rows_processed * o[0].n_extendable * (2 * p.bandwidth + 1) * 4.0 for o in outs)
     lanes = outs[0][0].lanes_per_instance
     bp = (outs[0][0].extended_bp, outs[1][0].extended_bp)
-    for d, o in zip((1, 0), outs):   # the pair launch must equal the reference's two-call form
-        alone = rc.extend(lib, d, fam.cores, sc, p)
-        same = (alone[0].rows_processed == o[0].rows_processed and alone[0].extended_bp == o[0].extended_bp and
-                np.array_equal(alone[1], o[1]) and np.array_equal(alone[2], o[2]) and np.array_equal(alone[3], o[3]))
-        if not same:
-            raise SystemExit(f"bench.py: pair launch differs from a separate ramcu_extend call (direction {d})")
+    # the timed job's outputs against the reference: rank 0's family is the one whose reference outputs are
+    # committed (tests/golden/full_config4.npz: the reference's extend_alignment() object code on exactly
+    # this input, 2 x 440 s of one core); other ranks / sizes compare with two separate ramcu_extend calls
+    checked = "two separate ramcu_extend calls"
+    golden = os.path.join(ROOT, "tests", "golden", "full_config4.npz")
+    if rank == 0 and n == WORKLOAD["n"] and flank == WORKLOAD["flank"] and os.path.exists(golden):
+        import hashlib
+        z = np.load(golden, allow_pickle=False)
+        meta = json.loads(str(z["meta"]))["seed4"]
+        if hashlib.sha256(fam.sequence.tobytes()).hexdigest() != meta["seq_sha"]:
+            raise SystemExit("bench.py: the generated family is not the one the reference golden was made from")
+        for d, o in zip((1, 0), outs):
+            rows = meta[f"rows{d}"]
+            if not (o[0].extended_bp == meta[f"bp{d}"] and o[0].rows_processed == rows and
+                    np.array_equal(o[1][:rows], z[f"seed4_master{d}"][:rows]) and
+                    np.array_equal(o[2], z[f"seed4_ext_len{d}"]) and np.array_equal(o[3], z[f"seed4_score_add{d}"])):
+                raise SystemExit(f"bench.py: outputs of the timed job differ from the reference golden (direction {d})")
+        checked = "outputs == reference golden (tests/golden/full_config4.npz)"
+    else:
+        for d, o in zip((1, 0), outs):
+            alone = rc.extend(lib, d, fam.cores, sc, p)
+            same = (alone[0].rows_processed == o[0].rows_processed and alone[0].extended_bp == o[0].extended_bp and
+                    np.array_equal(alone[1], o[1]) and np.array_equal(alone[2], o[2]) and np.array_equal(alone[3], o[3]))
+            if not same:
+                raise SystemExit(f"bench.py: pair launch differs from a separate ramcu_extend call (direction {d})")
 
     # ---- end-to-end leg: host buffers in, host results out, every step ---------------------------
     def step_e2e(verbose=False):
@@ -322,50 +467,41 @@ def run_cuda(args):
             feed_ms.append(f0.elapsed_time(f1))
         rc.free_library(hfeed)
     feed_bytes = dev_seq.numel() * (1.0 + 0.25 + 0.125)        # read 1 B/base, write 2 bit + 1 bit
-    feed_alloc = dev_seq.numel() * (0.25 + 0.125)             # the two output buffers are zero-filled first
+    feed_alloc = 0.0
     del dev_seq
 
-    # ---- config-5 style batch: many independent families sharing the GPU (families/s) -------------
-    fam_info = None
-    fam_stats = None
-    if args.families > 0:
-        # BASELINE configs[4] shape: a seeded sample of the 2 000-family mix, `--families` per GPU, sharded by
-        # family over the ranks (longest-processing-time-first, no communication between ranks)
-        specs = synth.config5_specs(5, 2000)
-        pick = sorted(np.random.default_rng(0).choice(len(specs), size=args.families * world, replace=False))
-        costs = [batch.family_cost(specs[i]["n"], specs[i]["params"]["bandwidth"], specs[i]["flank"]) for i in pick]
-        mine = batch.lpt_shard(costs, world)[rank]
-        fams5 = [synth.family_from_spec(specs[pick[i]]) for i in mine]
-        batch.extend_families(rc, fams5)          # warm-up: first use of every tiling in the mix loads its code
-        times5 = []
-        for _ in range(3):
-            barrier()
-            t0 = time.perf_counter()
-            res5 = batch.extend_families(rc, fams5)
-            torch.cuda.synchronize()
-            times5.append(time.perf_counter() - t0)
-        cu5 = sum(x.cell_updates for x in res5)
-        fam_stats = (float(np.median(times5)), float(len(fams5)), float(cu5), float(sum(f.n for f in fams5)))
-
+    n_bases = int(fam.sequence.size)
+    # the single-family leg is done: release it before the genome-scale round
     for j in jobs:
         rc.job_free(j)
     rc.free_library(lib)
+    jobs, lib = [], None
+    del host_seq, blob_pinned, fam
+
+    # ---- BASELINE configs[4]: the genome-scale round, sharded by family over the ranks -------------------
+    fam_info = None
+    fam_stats = None
+    if args.families != 0:
+        fam_stats, fam_extra = config5_round(args, rc, stream, world, rank, local, barrier, peak_gops)
 
     # ---- max over ranks -------------------------------------------------------------------------
     if fam_stats is not None:
+        # [device s, e2e s, families, cell updates, instances, generation s]
         fs = torch.tensor(fam_stats, dtype=torch.float64, device="cuda")
+        fmx, fsum = fs.clone(), fs.clone()
         if world > 1:
-            fmx = fs.clone()
             dist.all_reduce(fmx, op=dist.ReduceOp.MAX)
-            dist.all_reduce(fs, op=dist.ReduceOp.SUM)
-            fs[0] = fmx[0]
-        dt5, nf5, cu5, ni5 = (float(x) for x in fs)
-        fam_info = {"n_families": int(nf5), "instances": int(ni5), "families_per_s": round(nf5 / dt5, 2),
-                    "gcups_e2e": round(cu5 / dt5 / 1e9, 1), "seconds": round(dt5, 3),
-                    "what": "seeded sample of the BASELINE configs[4] family mix (N 100-10k log-uniform, "
-                            "bandwidth 20-100, flank 0.5-5 kb), %d families per GPU sharded by family (LPT) over "
-                            "the ranks, host buffers in / host results out; per rank the median of three runs "
-                            "after one warm-up run, max over ranks" % args.families}
+            dist.all_reduce(fsum, op=dist.ReduceOp.SUM)
+        dev5, e2e5, gen5 = float(fmx[0]), float(fmx[1]), float(fmx[5])
+        nf5, cu5, ni5 = float(fsum[2]), float(fsum[3]), float(fsum[4])
+        fam_info = dict(fam_extra, n_families=int(nf5), instances=int(ni5), cell_updates=cu5,
+                        seconds_device=round(dev5, 3), seconds_e2e=round(e2e5, 3),
+                        families_per_s=round(nf5 / e2e5, 2), families_per_s_device=round(nf5 / dev5, 2),
+                        gcups=round(cu5 / dev5 / 1e9, 1), gcups_e2e=round(cu5 / e2e5 / 1e9, 1),
+                        # LPT balance: busy time of the ranks (device seconds), max over mean
+                        rank_busy_max_over_mean=round(dev5 / (float(fsum[0]) / world), 4),
+                        roofline_frac=round(cu5 / dev5 / 1e9 * OPS_PER_CU / world / peak_gops, 4),
+                        generation_seconds=round(gen5, 1), scaling="strong")
     stats = torch.tensor([dev_ms, e2e_s, cu_step, e2e2_s], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
@@ -392,7 +528,7 @@ def run_cuda(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
-        tf = "r1_extend_kernel_traffic.json" if args.sequential else "r1_extend_kernel_pair_traffic.json"
+        tf = "r2_extend_kernel_traffic.json" if args.sequential else "r2_extend_kernel_pair_traffic.json"
         traffic = json.load(open(os.path.join(ROOT, "profiles", tf)))["dram_bytes_per_launch"]
     except Exception:
         pass
@@ -400,21 +536,22 @@ def run_cuda(args):
     cpu = None
     if world == 1 or rank == 0:
         cores = os.cpu_count() or 1
-        agg, single, kind, wall = cpu_baseline(args.cpu_instances, WORKLOAD["flank"], cores)
+        per_step, kind, wall = cpu_baseline(cores, steps=2)
+        agg, single = per_step[-1][0], per_step[-1][1]
         cpu = {"value": round(agg, 4), "unit": "GCUPS", "cores": cores, "kind": kind,
-               "single_process_value": round(single, 4),
-               "sample": f"{cores} processes at once, each one synthetic family of {args.cpu_instances} instances x "
-                         f"{WORKLOAD['flank']} bp flanks (config-4 shape), reference extend_alignment() object "
-                         f"code timed with clock_gettime around the two calls ({wall:.1f}s wall)"}
+               "single_process_value": round(single, 4), "sample": cpu_sample_text(cores) + f" ({wall:.0f} s wall)",
+               "full_config4_single_process": FULL_CONFIG4_CPU}
 
     line = {"metric": "banded_dp_gcups", "value": round(gcups, 1), "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": dict(workload_config(world), instances=n, flank_bp=flank,
-                                                lanes_per_instance=lanes, extended_bp=list(bp),
-                                                passes="two launches, right then left" if args.sequential else
-                                                "right and left pass in one launch (independent here: every "
-                                                "instance is its own sequence; checked against separate calls)"),
+            "data": "synthetic", "config": dict(workload_config(world), instances=n, flank_bp=flank),
+            "details": {"lanes_per_instance": lanes, "extended_bp": list(bp), "parity": checked,
+                        "passes": "two launches, right then left" if args.sequential else
+                                  "right and left pass of the family in the same threads, taking turns row by row "
+                                  "(independent here: every instance is its own sequence)",
+                        "timing": "CUDA events on the launching stream around each step, L2 flushed between steps "
+                                  "(256 MiB write), max over ranks"},
             "families_per_s": round(world * args.steps / (dev_ms * 1e-3), 2),
             "roofline": {"bound": "int32_alu", "achieved": round(per_gpu_gops, 1), "peak": round(peak_gops, 1),
                          "unit": "Gop/s", "frac": round(per_gpu_gops / peak_gops, 4),
@@ -429,7 +566,7 @@ def run_cuda(args):
                                  "note": "algorithmic flank bytes (2 bits per base per instance-row); the path is "
                                          "ALU bound, HBM is a sanity figure"}},
             "flank_feed": {"kernel": "pack_library_kernel (1 byte/base codes in HBM -> 2 bit/base + N mask), with the "
-                                     "zero-fill of its two output buffers", "bases": int(fam.sequence.size),
+                                     "initialisation of the slack around its two output buffers", "bases": n_bases,
                            "ms": round(float(np.median(feed_ms)), 4),
                            "achieved": round((feed_bytes + feed_alloc) / (float(np.median(feed_ms)) * 1e-3) / 1e9, 1),
                            "peak": hbm_peak, "unit": "GB/s",
@@ -467,8 +604,10 @@ def main():
     ap.add_argument("--sequential", action="store_true",
                     help="time the right and the left pass as two launches (the form the unchanged CLI uses when "
                          "overlap avoidance may apply) instead of the pair launch")
-    ap.add_argument("--families", type=int, default=12, help="size of the config-5 family-batch sample (0 = skip)")
-    ap.add_argument("--cpu-instances", type=int, default=48, help="instances of the CPU-baseline sample family")
+    ap.add_argument("--families", type=int, default=-1,
+                    help="genome-scale round (BASELINE configs[4]): -1 = all 2000 families, K > 0 = a seeded subset of K, "
+                         "0 = skip")
+    ap.add_argument("--family-runs", type=int, default=2, help="timed runs of the genome-scale round per leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

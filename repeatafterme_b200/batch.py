@@ -55,7 +55,8 @@ def _as_dict(res, master, ext_len, score_add, bandwidth):
 
 
 def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
-    """Extend a list of families (objects with .sequence, .cores, .params as in synth.Family).
+    """Extend a list of families (objects with .sequence or .blob, .cores, .params: synth.Family or
+    synth.PackedFamily).
     Host buffers in, host results out: library upload, every pass of every family as one batch
     (or right batch, `between_passes` hook, left batch), fetch."""
     libs, scs, prs = [], [], []
@@ -69,7 +70,10 @@ def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
             p["concurrent_instances"] = total - int(f.cores.size)
         scs.append(sc)
         prs.append(make_params(**p))
-        libs.append(rc.upload_library(f.sequence))
+        if hasattr(f, "blob"):   # synth.PackedFamily: 2 bits per base, decoded on the device
+            libs.append(rc.library_from_twobit(f.blob, f.windows, f.n_start, f.n_len, f.total))
+        else:
+            libs.append(rc.upload_library(f.sequence))
     results = [FamilyResult() for _ in fams]
     try:
         # Without a between-passes step (the overlap avoidance of ram_extend.c:445-499 belongs to the

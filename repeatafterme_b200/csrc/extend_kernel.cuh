@@ -354,9 +354,9 @@ constexpr int kRedStride = 1;      // 64-bit words between the accumulators of o
 // the CTAs' contributions, delivery of the column sums to every warp -- without a CTA barrier
 // ---------------------------------------------------------------------------------------------
 // Column c uses slot c & 1. Contribution: lane 0 of every warp adds its four partial sums to
-// acc[slot] (shared-memory atomics) and then counts itself in cnt[slot]; the warp that counts last
-// owns the CTA's sums: it clears the slot and either publishes them (family on one CTA) or adds them
-// to the column's global accumulators (one RED per candidate, the arrival count in the upper bits).
+// acc[slot] (shared-memory atomics); after the one CTA barrier of the row and pass, warp 0 owns the CTA's sums:
+// it clears the slot and either publishes them (family on one CTA) or adds them to the column's
+// global accumulators (one RED per candidate, the arrival count in the upper bits).
 // Delivery: warp 0 polls the global accumulators and publishes the complete sums; every warp waits
 // for res_tag[slot] == c + 1 when it next needs the column, i.e. after it has done the other pass's
 // row in between. A slot is reused two columns later, which every warp of the CTA can only reach
@@ -365,7 +365,6 @@ struct PassShared
 {
   int acc[2][4];
   int res[2][4];
-  int cnt[2];
   int res_tag[2];
 };
 
@@ -398,6 +397,19 @@ __device__ __forceinline__ void spin_timeout()
   abort();
 #else
   __trap();
+#endif
+}
+
+// RAMCU_STATS: time stamps of the exchange of kStatCols columns of the first pass (globaltimer, ns)
+constexpr int kStatCol0 = 1024, kStatCols = 64;
+__device__ __forceinline__ long long global_ns()
+{
+#ifdef RAMCU_EMUL
+  return 0;
+#else
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 #endif
 }
 
@@ -484,7 +496,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
 
   const FamDev *Fp[NP];
   PassRegs<C> ps[NP];
-  bool dbg_on[NP], use_fast[NP];
+  bool dbg_on[NP], use_fast[NP], has_forced[NP], has_dbg_best[NP], has_dbg_path[NP];
 
   // ---- set-up of every pass: instance, boundary row, first base window ------------------------
 #pragma unroll
@@ -508,6 +520,9 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     S.tmin = I.tmin;
     S.tmax = I.tmax;
     dbg_on[p] = (F->dbg_rows != nullptr) || (F->dbg_path != nullptr);
+    has_forced[p] = F->forced != nullptr;
+    has_dbg_best[p] = F->dbg_best != nullptr;
+    has_dbg_path[p] = F->dbg_path != nullptr;
     use_fast[p] = (WS != 0) && gaps_ok && !dbg_on[p];
 #pragma unroll
     for (int i = 0; i < CW; ++i)
@@ -650,35 +665,30 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     }
     PassShared &H = sh.ps[p];
     const int slot = r & 1;
-    int last = 0;
-    if (lane == 0)
+    const bool sender = (warp == 0);
+    if (nwarps > 1)
     {
-      if (nwarps > 1)
+      if (lane == 0)
       {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
           atomicAdd(&H.acc[slot][a], c[a]);
-        __threadfence_block();
-        last = (atomicAdd(&H.cnt[slot], 1) == nwarps - 1) ? 1 : 0;
       }
-      else
-        last = 1;
+      // One CTA barrier per row and pass; warp 0 then owns the CTA's sums. (Letting the warp that
+      // arrives last send instead, with no barrier at all, measured the same for two passes per thread
+      // and 5 % slower for one.)
+      __syncthreads();
     }
-    last = __shfl_sync(kFull, last, 0);
-    if (last)
+    if (sender)
     {
-      // this warp counted last: it owns the CTA's sums of the column
       int mine = 0;
       if (nwarps > 1)
       {
-        __threadfence_block();
         if (lane < 4)
         {
           mine = ld_volatile_shared(&H.acc[slot][lane]);
-          st_volatile_shared(&H.acc[slot][lane], 0);
+          st_volatile_shared(&H.acc[slot][lane], 0);   // next used two columns (two barriers) later
         }
-        if (lane == 0)
-          st_volatile_shared(&H.cnt[slot], 0);
       }
       else
         mine = sel4(lane & 3, c[0], c[1], c[2], c[3]);
@@ -687,6 +697,10 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         if (lane < 4)   // column r owns four accumulators: (arrivals << 48 | sum), zeroed before the launch
           atomicAdd(F->slots + (size_t) r * 4 * kRedStride + lane * kRedStride,
                     (1ull << 48) | (unsigned long long) (unsigned) mine);
+#ifndef RAMCU_EMUL
+        if (stats && p == 0 && lane == 0 && r >= kStatCol0 && r < kStatCol0 + kStatCols)
+          F0->dbg_wait[2 * n_ctas + ((size_t) (r - kStatCol0) * n_ctas + cta_in_fam) * 3] = global_ns();
+#endif
       }
       else
       {
@@ -700,6 +714,18 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     }
   };
 
+  // ---- warp 0 asks for the accumulators of a column ahead of time: the load is in flight while the
+  //      other pass's row is computed, so that the receive below rarely waits for an L2 round trip -------
+  unsigned long long pre[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+    pre[p] = 0;
+  auto prefetch = [&](auto pc, const int r) {
+    constexpr int p = decltype(pc)::value;
+    if (n_ctas > 1 && warp == 0 && lane < 4 && ps[p].active)
+      pre[p] = ld_relaxed_u64(Fp[p]->slots + (size_t) r * 4 * kRedStride + lane * kRedStride);
+  };
+
   // ---- the column sums of row r arrive --------------------------------------------------------------
   auto receive = [&](auto pc, const int r, int (&sums)[4]) {
     constexpr int p = decltype(pc)::value;
@@ -710,19 +736,23 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     {
 #ifndef RAMCU_EMUL
       const long long t0 = stats ? clock64() : 0;
+      const bool stamp = stats && p == 0 && lane == 0 && r >= kStatCol0 && r < kStatCol0 + kStatCols;
+      if (stamp)
+        F0->dbg_wait[2 * n_ctas + ((size_t) (r - kStatCol0) * n_ctas + cta_in_fam) * 3 + 1] = global_ns();
 #endif
       unsigned lo = 0;
       if (lane < 4)
       {
         const unsigned long long *word = F->slots + (size_t) r * 4 * kRedStride + lane * kRedStride;
-        unsigned long long v;
+        unsigned long long v = pre[p];   // asked for during the other pass's row (0 if not)
+        pre[p] = 0;
         unsigned spins = 0;
-        do
+        while ((int) (v >> 48) != n_ctas)
         {
           v = ld_relaxed_u64(word);
           if (++spins > kMaxGlobalSpins)
             spin_timeout();   // a CTA of this family never became resident (something else holds the SMs)
-        } while ((int) (v >> 48) != n_ctas);
+        }
         lo = (unsigned) v;
         st_volatile_shared(&H.res[slot][lane], (int) lo);
       }
@@ -733,6 +763,8 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
 #ifndef RAMCU_EMUL
       if (stats)
         t_wait += clock64() - t0;
+      if (stamp)
+        F0->dbg_wait[2 * n_ctas + ((size_t) (r - kStatCol0) * n_ctas + cta_in_fam) * 3 + 2] = global_ns();
 #endif
     }
     {
@@ -769,12 +801,12 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         besta = a;
       }
     }
-    if (F->forced != nullptr)
+    if (has_forced[p])
     {
       besta = F->forced[r] & 3;
       curr = sel4(besta, sums[0], sums[1], sums[2], sums[3]);
     }
-    if (F->dbg_best != nullptr)
+    if (has_dbg_best[p])
     {
       if (S.valid && gl == 0)
       {
@@ -910,7 +942,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         S.high = bestb;
         S.pos = r - B + kidx;
       }
-      if (F->dbg_path != nullptr && S.valid && gl == 0)
+      if (has_dbg_path[p] && S.valid && gl == 0)
         F->dbg_idx[(size_t) r * n_ext + S.inst] = kidx;
     }
 
@@ -964,6 +996,8 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       int sums[4];
       receive(PassTag<0>(), r, sums);
       commit(PassTag<0>(), r, sums);
+      if (NP > 1)
+        prefetch(PassTag<NP - 1>(), r);
       if (ps[0].active)
         sweep_and_send(PassTag<0>(), r + 1);
       any = true;
@@ -973,6 +1007,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       int sums[4];
       receive(PassTag<NP - 1>(), r, sums);
       commit(PassTag<NP - 1>(), r, sums);
+      prefetch(PassTag<0>(), r + 1);
       if (ps[NP - 1].active)
         sweep_and_send(PassTag<NP - 1>(), r + 1);
       any = true;

@@ -812,8 +812,9 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     }
     if (getenv("RAMCU_STATS"))
     {
-      CKJ(cudaMallocAsync(&j->d_dbg_wait, (size_t) 2 * max_ctas * sizeof(long long), c->stream));
-      CKJ(cudaMemsetAsync(j->d_dbg_wait, 0, (size_t) 2 * max_ctas * sizeof(long long), c->stream));
+      const size_t nw = (size_t) (2 + 3 * kStatCols) * max_ctas;
+      CKJ(cudaMallocAsync(&j->d_dbg_wait, nw * sizeof(long long), c->stream));
+      CKJ(cudaMemsetAsync(j->d_dbg_wait, 0, nw * sizeof(long long), c->stream));
     }
     FamDev &f = j->fam;
     fill_family(f, sc, pr, j->n_ext, j->n_ctas);
@@ -983,7 +984,7 @@ extern "C" int ramcu_job_fetch(ramcu_ctx *c, ramcu_job *j, uint8_t *master_out, 
   if (j->d_dbg_wait && j->stats_ctas > 0)
   {
     const int n_stat = j->stats_ctas;
-    std::vector<long long> w((size_t) 2 * n_stat);
+    std::vector<long long> w((size_t) (2 + 3 * kStatCols) * n_stat);
     CK(cudaMemcpy(w.data(), j->d_dbg_wait, w.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     long long wmin = 1LL << 62, wmax = 0, wsum = 0, tmax = 0;
     int n_seen = 0;
@@ -1000,6 +1001,47 @@ extern "C" int ramcu_job_fetch(ramcu_ctx *c, ramcu_job *j, uint8_t *master_out, 
     fprintf(stderr, "[ramcu stats] ctas=%d rows=%d cycles/row: total %.0f, warp 0 waiting for the column sums: min %.0f avg %.0f max %.0f\n",
             n_seen, r4[1], (double) tmax / std::max(r4[1], 1), (double) wmin / std::max(r4[1], 1),
             (double) wsum / std::max(n_seen, 1) / std::max(r4[1], 1), (double) wmax / std::max(r4[1], 1));
+    if (const char *dump = getenv("RAMCU_STATS_DUMP"))
+    {
+      FILE *fh = fopen(dump, "ab");
+      if (fh)
+      {
+        const long long hdr[2] = {n_stat, kStatCols};
+        fwrite(hdr, sizeof(long long), 2, fh);
+        fwrite(w.data(), sizeof(long long), w.size(), fh);
+        fclose(fh);
+      }
+    }
+    if (n_stat > 1 && r4[1] > kStatCol0 + kStatCols)
+    {
+      // exchange of the sampled columns: when the CTAs sent (spread = skew between CTAs), when the
+      // pollers arrived, when the sums were there
+      double skew = 0, lat_first = 0, lat_mean = 0, poll_lead = 0;
+      for (int cidx = 0; cidx < kStatCols; ++cidx)
+      {
+        const long long *t = w.data() + 2 * n_stat + (size_t) cidx * n_stat * 3;
+        long long smin = 1LL << 62, smax = 0, rmin = 1LL << 62;
+        for (int i = 0; i < n_stat; ++i)
+        {
+          smin = std::min(smin, t[3 * i]);
+          smax = std::max(smax, t[3 * i]);
+          rmin = std::min(rmin, t[3 * i + 2]);
+        }
+        double rsum = 0, psum = 0;
+        for (int i = 0; i < n_stat; ++i)
+        {
+          rsum += (double) (t[3 * i + 2] - smax);
+          psum += (double) (t[3 * i + 1] - smax);
+        }
+        skew += (double) (smax - smin);
+        lat_first += (double) (rmin - smax);
+        lat_mean += rsum / n_stat;
+        poll_lead += psum / n_stat;
+      }
+      fprintf(stderr, "[ramcu stats] exchange of %d columns (ns): send skew %.0f, last send -> first ready %.0f, -> mean ready %.0f, "
+              "mean poll start - last send %.0f\n", kStatCols, skew / kStatCols, lat_first / kStatCols, lat_mean / kStatCols,
+              poll_lead / kStatCols);
+    }
   }
   if (master_out && r4[1] > 0)
     memcpy(master_out, hm, r4[1]);

@@ -306,3 +306,60 @@ def config5_parity_sample(specs=None, seed: int = 11):
                       if s["n"] >= 5000 and s["params"]["bandwidth"] == bw and i not in pick), key=cu)
         pick.append(big[0])
     return sorted(pick)
+
+
+@dataclass
+class PackedFamily:
+    """A family whose library travels as the .2bit file stores DNA (4 bases per byte, first base in the
+    top bits, T0 C1 A2 G3 -- kentsrc/twoBitNew.c:571-582) instead of the loader's byte per base: one
+    record holding the concatenated windows + the N runs, in library coordinates."""
+
+    blob: np.ndarray        # uint8, ceil(total / 4) bytes
+    total: int              # bases
+    n_start: np.ndarray     # uint64 N runs (library coordinates)
+    n_len: np.ndarray
+    cores: np.ndarray       # CORE_DTYPE[n]
+    params: dict = field(default_factory=dict)
+
+    @property
+    def n(self) -> int:
+        return int(self.cores.size)
+
+    @property
+    def windows(self) -> np.ndarray:
+        return np.array([[0, self.total, 0, 0]], dtype=np.uint64)
+
+
+def pack_family(fam: Family) -> PackedFamily:
+    seq = np.asarray(fam.sequence, dtype=np.uint8)
+    isn = seq > 3
+    if isn.any():
+        d = np.diff(np.concatenate([[0], isn.astype(np.int8), [0]]))
+        n_start = np.flatnonzero(d == 1).astype(np.uint64)
+        n_len = (np.flatnonzero(d == -1) - np.flatnonzero(d == 1)).astype(np.uint64)
+    else:
+        n_start = np.zeros(0, dtype=np.uint64)
+        n_len = np.zeros(0, dtype=np.uint64)
+    return PackedFamily(blob=pack_twobit_record(seq), total=int(seq.size), n_start=n_start, n_len=n_len,
+                        cores=fam.cores, params=dict(fam.params))
+
+
+def _packed_from_spec(spec):
+    return pack_family(family_from_spec(spec))
+
+
+def generate_packed_families(specs, procs: int = 0):
+    """family_from_spec + pack_family for a list of specs on `procs` worker processes (generation is
+    a Python loop per instance: ~30 ns per base on one core)"""
+    import multiprocessing as mp
+    import os
+    procs = procs or max(1, (os.cpu_count() or 1))
+    if procs == 1 or len(specs) <= 1:
+        return [_packed_from_spec(s) for s in specs]
+    # largest first so that the pool's tail is short
+    order = sorted(range(len(specs)), key=lambda i: -specs[i]["n"] * specs[i]["flank"])
+    out = [None] * len(specs)
+    with mp.get_context("fork").Pool(procs) as pool:
+        for i, pf in zip(order, pool.imap(_packed_from_spec, [specs[i] for i in order], chunksize=1)):
+            out[i] = pf
+    return out

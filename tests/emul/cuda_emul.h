@@ -78,6 +78,16 @@ static inline int __all_sync(unsigned, int pred)
   pthread_barrier_wait(&emul_warp->bar);
   return all;
 }
+static inline unsigned __ballot_sync(unsigned, int pred)
+{
+  const int lane = threadIdx.x & 31;
+  emul_warp->buf[lane] = pred ? 1 : 0;
+  pthread_barrier_wait(&emul_warp->bar);
+  unsigned m = 0;
+  for (int i = 0; i < 32; ++i) m |= (unsigned) (emul_warp->buf[i] & 1) << i;
+  pthread_barrier_wait(&emul_warp->bar);
+  return m;
+}
 static inline int __reduce_add_sync(unsigned, int v)
 {
   const int lane = threadIdx.x & 31;

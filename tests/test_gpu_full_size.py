@@ -46,7 +46,7 @@ def test_config4_full_equals_reference(ramcu):
         pair = ramcu.extend_pair(lib, fam.cores, sc, p)
         for d, o in zip((1, 0), pair):
             _check(case["want"][d], _got(*o), f"pair launch dir={d}")
-        for G in (0, 4):
+        for G in (0, 5):
             _, pg = _params(case, lanes_per_instance=G)
             for d in (1, 0):
                 _check(case["want"][d], _got(*ramcu.extend(lib, d, fam.cores, sc, pg)), f"G={G} dir={d}")
