@@ -1,8 +1,9 @@
 """In-tree build of the native pieces (nvcc cross-compiles sm_100a without a GPU).
 
   csrc/libramcu.so   CUDA kernels + extern "C" ABI (include/ramcu.h)          -- the product
-  bin/RAMExtend      the reference's own host objects with extend_alignment() replaced by
-                     csrc/ramx_boundary.c (only when oracle/_ref/obj exists)     -- the product CLI
+  bin/RAMExtend      the reference's own host code (compiled out of tree into host/_refobj when
+                     /root/reference is present) with extend_alignment(), the flank loader and the DP
+                     scratch allocation replaced (csrc/ramx_boundary.c, csrc/ramx_loader.c)  -- the product CLI
 """
 from __future__ import annotations
 
@@ -65,35 +66,62 @@ def build_libramcu(force=False, verbose=False):
     return out
 
 
+REF_HOST_SRC = ["ram_extend", "common", "report", "score_system", "cmd_line_opts", "version", "sequence"]
+KENT_SRC = ["twoBitNew", "common", "memalloc", "hash", "errAbort", "obscure", "localmem", "dnautil", "dlist", "dystring",
+            "linefile", "options", "verbose", "fa", "dnaseq", "bits"]
+
+
 def build_cli(force=False):
-    """Link bin/RAMExtend = reference host objects (compiled out of tree by oracle/Makefile from
-    /root/reference, extend_alignment weakened) + our boundary + libramcu.so."""
-    obj_dir = os.path.join(ROOT, "oracle", "_ref", "obj")
-    boundary = os.path.join(CSRC, "ramx_boundary.c")
-    if not os.path.isdir(obj_dir) or not os.path.exists(boundary):
-        return None
+    """bin/RAMExtend = the reference's own host code (main, flag parsing, report, every output; compiled
+    out of tree from /root/reference into host/_refobj, nothing copied) with three symbols replaced:
+    extend_alignment() by csrc/ramx_boundary.c (the GPU path), loadSequenceSubsetMinimal() and
+    allocate_score() by csrc/ramx_loader.c. The reference's DP object (bnw_extend.o) is not linked.
+    Also host/_refobj/libramxload.so: the product loader behind a flat entry point, for the tests."""
+    ref = os.environ.get("RAM_REFERENCE", "/root/reference")
+    obj_dir = os.path.join(HERE, "host", "_refobj")
     bin_dir = os.path.join(HERE, "bin")
-    os.makedirs(bin_dir, exist_ok=True)
     out = os.path.join(bin_dir, "RAMExtend")
-    ref_objs = ["ram_extend", "common", "report", "score_system", "cmd_line_opts", "version",
-                "sequence", "bnw_extend"]
-    srcs = [boundary, os.path.join(CSRC, "libramcu.so")] + [os.path.join(obj_dir, o + ".o") for o in ref_objs]
-    if not force and not _newer(out, srcs):
+    have_ref = os.path.exists(os.path.join(ref, "ram_extend.c"))
+    if not have_ref:
+        return out if os.path.exists(out) else None   # GPU box: the prebuilt binary travels
+    os.makedirs(obj_dir, exist_ok=True)
+    os.makedirs(bin_dir, exist_ok=True)
+    gcc = "/usr/bin/gcc"
+    ours = [os.path.join(CSRC, f) for f in ("ramx_boundary.c", "ramx_loader.c", "ramx_loader_flat.c", "ramx_loader.h")]
+    ours.append(os.path.join(ROOT, "include", "ramcu.h"))
+    if not force and os.path.exists(out) and not _newer(out, ours + [os.path.join(CSRC, "libramcu.so")]):
         return out
-    weak = os.path.join(bin_dir, "ram_extend_weak.o")
-    subprocess.check_call(["objcopy", "--weaken-symbol=extend_alignment",
-                           os.path.join(obj_dir, "ram_extend.o"), weak])
-    bobj = os.path.join(bin_dir, "ramx_boundary.o")
-    ref_inc = os.environ.get("RAM_REFERENCE", "/root/reference")
-    if not os.path.exists(os.path.join(ref_inc, "common.h")):
-        return out if os.path.exists(out) else None
-    subprocess.check_call(["/usr/bin/gcc", "-std=gnu11", "-O2", "-fpic", "-Wall", "-I" + ref_inc,
-                           "-I" + os.path.join(ref_inc, "minunit"), "-I" + os.path.join(ROOT, "include"),
-                           "-c", boundary, "-o", bobj])
-    objs = [weak] + [os.path.join(obj_dir, o + ".o") for o in ref_objs if o != "ram_extend"]
-    subprocess.check_call(["/usr/bin/gcc", "-o", out, bobj, *objs,
-                           "-L" + os.path.join(ROOT, "oracle", "_ref"), "-lTwoBit", "-lm",
-                           "-L" + CSRC, "-lramcu", "-Wl,-rpath,$ORIGIN/../csrc"])
+    jobs = []
+    for name in REF_HOST_SRC:   # the reference's flags (Makefile:16)
+        o = os.path.join(obj_dir, name + ".o")
+        if force or not os.path.exists(o):
+            jobs.append([gcc, "-std=gnu11", "-fpic", "-mtune=native", "-g", "-O3", "-w", "-I" + os.path.join(ref, "minunit"),
+                         "-I" + ref, "-c", os.path.join(ref, name + ".c"), "-o", o])
+    for name in KENT_SRC:
+        o = os.path.join(obj_dir, "kent_" + name + ".o")
+        if force or not os.path.exists(o):
+            jobs.append([gcc, "-g", "-fpic", "-O2", "-w", "-I" + os.path.join(ref, "kentsrc"), "-c",
+                         os.path.join(ref, "kentsrc", name + ".c"), "-o", o])
+    inc = ["-I" + ref, "-I" + os.path.join(ref, "minunit"), "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+    for name in ("ramx_boundary", "ramx_loader", "ramx_loader_flat"):
+        jobs.append([gcc, "-std=gnu11", "-O2", "-fpic", "-Wall", *inc, "-c", os.path.join(CSRC, name + ".c"),
+                     "-o", os.path.join(obj_dir, name + ".o")])
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        list(ex.map(subprocess.check_call, jobs))
+    weak_main = os.path.join(obj_dir, "ram_extend_weak.o")
+    subprocess.check_call(["objcopy", "--weaken-symbol=extend_alignment", os.path.join(obj_dir, "ram_extend.o"), weak_main])
+    weak_seq = os.path.join(obj_dir, "sequence_weak.o")
+    subprocess.check_call(["objcopy", "--weaken-symbol=loadSequenceSubsetMinimal", os.path.join(obj_dir, "sequence.o"), weak_seq])
+    kent = os.path.join(obj_dir, "libTwoBit.a")
+    if os.path.exists(kent):
+        os.remove(kent)
+    subprocess.check_call(["ar", "rcs", kent] + [os.path.join(obj_dir, "kent_" + k + ".o") for k in KENT_SRC])
+    objs = [weak_main, weak_seq] + [os.path.join(obj_dir, o + ".o") for o in REF_HOST_SRC if o not in ("ram_extend", "sequence")]
+    subprocess.check_call([gcc, "-o", out, os.path.join(obj_dir, "ramx_boundary.o"), os.path.join(obj_dir, "ramx_loader.o"),
+                           *objs, "-L" + obj_dir, "-lTwoBit", "-lm", "-L" + CSRC, "-lramcu", "-Wl,-rpath,$ORIGIN/../csrc"])
+    subprocess.check_call([gcc, "-shared", "-o", os.path.join(obj_dir, "libramxload.so"),
+                           os.path.join(obj_dir, "ramx_loader.o"), os.path.join(obj_dir, "ramx_loader_flat.o")])
     return out
 
 

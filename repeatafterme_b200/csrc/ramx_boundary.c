@@ -30,6 +30,7 @@
 #include <string.h>
 #include <stdint.h>
 #include <ctype.h>
+#include <time.h>
 
 #include "common.h"        /* struct coreAlignment        (reference, -I$(REF)) */
 #include "sequence.h"      /* struct sequenceLibrary, SYM_N */
@@ -37,6 +38,7 @@
 #include "ram_extend.h"
 
 #include "ramcu.h"
+#include "ramx_loader.h"
 
 /* globals of ram_extend.c that extend_alignment() reads (ram_extend.c:40,52,61) */
 extern int VERBOSE;
@@ -60,6 +62,14 @@ static struct
   int32_t *ext_len, *score_add;
   ramcu_result_t res;
 } g_ahead;
+
+static double
+now_s(void)
+{
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec;
+}
 
 static void
 ahead_drop(void)
@@ -108,11 +118,16 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
     exit(1);
   }
 
+  const int timing = getenv("RAMX_TIMING") != NULL;
+  double t0 = now_s();
   if (g_ctx == NULL)
   {
     const char *dev = getenv("RAMCU_DEVICE");
     if (ramcu_init(dev ? atoi(dev) : 0, &g_ctx) != RAMCU_OK)
       die("ramcu_init");
+    if (timing)
+      fprintf(stderr, "[ramx timing] CUDA context + kernel images %.3f s\n", now_s() - t0);
+    t0 = now_s();
   }
   /* the right and the left pass share one library upload */
   if (g_lib == NULL || g_lib_seq != seqLib->sequence || g_lib_len != seqLib->length)
@@ -120,11 +135,26 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
     ahead_drop();
     if (g_lib)
       ramcu_library_free(g_ctx, g_lib);
-    if (ramcu_library_upload(g_ctx, (const uint8_t *) seqLib->sequence, seqLib->length, &g_lib) !=
-        RAMCU_OK)
-      die("ramcu_library_upload");
+    {
+      /* a library built by the product loader travels as the .2bit file's own packed bytes and is
+       * decoded on the device; any other library (1 byte per base) is packed on the device */
+      const struct ramx_twobit_source *src =
+        getenv("RAMCU_BYTE_LIBRARY") ? NULL : ramx_loader_source(seqLib->sequence, seqLib->length);
+      if (src != NULL)
+      {
+        if (ramcu_library_from_twobit(g_ctx, src->blob, src->blob_bytes, src->n_windows,
+                                      (const ramcu_window_t *) src->windows, src->n_nranges, src->n_start,
+                                      src->n_len, src->total, &g_lib) != RAMCU_OK)
+          die("ramcu_library_from_twobit");
+      }
+      else if (ramcu_library_upload(g_ctx, (const uint8_t *) seqLib->sequence, seqLib->length, &g_lib) != RAMCU_OK)
+        die("ramcu_library_upload");
+    }
     g_lib_seq = seqLib->sequence;
     g_lib_len = seqLib->length;
+    if (timing)
+      fprintf(stderr, "[ramx timing] library to the device %.3f s\n", now_s() - t0);
+    t0 = now_s();
   }
 
   /* matrix[cons][A,C,G,T,N]; the soft-masked columns 4..7 must score like N (they do for every
@@ -272,6 +302,9 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
     }
   }
 
+  if (timing)
+    fprintf(stderr, "[ramx timing] extend_alignment(%s) %.3f s (kernel %.1f ms)\n", direction ? "right" : "left",
+            now_s() - t0, res.kernel_ms);
   /* consensus of every processed row (ram_extend.c:1092-1095) */
   for (r = 0; r < res.rows_processed; r++)
   {
