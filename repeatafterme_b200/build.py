@@ -87,7 +87,8 @@ def build_cli(force=False):
     os.makedirs(obj_dir, exist_ok=True)
     os.makedirs(bin_dir, exist_ok=True)
     gcc = "/usr/bin/gcc"
-    ours = [os.path.join(CSRC, f) for f in ("ramx_boundary.c", "ramx_loader.c", "ramx_loader_flat.c", "ramx_loader.h")]
+    ours = [os.path.join(CSRC, f) for f in ("ramx_boundary.c", "ramx_loader.c", "ramx_loader_flat.c", "ramx_loader.h",
+                                            "ramx_boundary.h", "ramx_batch.c")]
     ours.append(os.path.join(ROOT, "include", "ramcu.h"))
     if not force and os.path.exists(out) and not _newer(out, ours + [os.path.join(CSRC, "libramcu.so")]):
         return out
@@ -103,7 +104,7 @@ def build_cli(force=False):
             jobs.append([gcc, "-g", "-fpic", "-O2", "-w", "-I" + os.path.join(ref, "kentsrc"), "-c",
                          os.path.join(ref, "kentsrc", name + ".c"), "-o", o])
     inc = ["-I" + ref, "-I" + os.path.join(ref, "minunit"), "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
-    for name in ("ramx_boundary", "ramx_loader", "ramx_loader_flat"):
+    for name in ("ramx_boundary", "ramx_loader", "ramx_loader_flat", "ramx_batch"):
         jobs.append([gcc, "-std=gnu11", "-O2", "-fpic", "-Wall", *inc, "-c", os.path.join(CSRC, name + ".c"),
                      "-o", os.path.join(obj_dir, name + ".o")])
     from concurrent.futures import ThreadPoolExecutor
@@ -120,6 +121,13 @@ def build_cli(force=False):
     objs = [weak_main, weak_seq] + [os.path.join(obj_dir, o + ".o") for o in REF_HOST_SRC if o not in ("ram_extend", "sequence")]
     subprocess.check_call([gcc, "-o", out, os.path.join(obj_dir, "ramx_boundary.o"), os.path.join(obj_dir, "ramx_loader.o"),
                            *objs, "-L" + obj_dir, "-lTwoBit", "-lm", "-L" + CSRC, "-lramcu", "-Wl,-rpath,$ORIGIN/../csrc"])
+    # bin/RAMExtendBatch: the same objects with the reference's main() renamed, driven by csrc/ramx_batch.c
+    batch_main = os.path.join(obj_dir, "ram_extend_batch.o")
+    subprocess.check_call(["objcopy", "--redefine-sym", "main=ramref_main", weak_main, batch_main])
+    subprocess.check_call([gcc, "-o", os.path.join(bin_dir, "RAMExtendBatch"), os.path.join(obj_dir, "ramx_batch.o"),
+                           os.path.join(obj_dir, "ramx_boundary.o"), os.path.join(obj_dir, "ramx_loader.o"), batch_main,
+                           *objs[1:], "-L" + obj_dir, "-lTwoBit", "-lm", "-L" + CSRC, "-lramcu",
+                           "-Wl,-rpath,$ORIGIN/../csrc"])
     subprocess.check_call([gcc, "-shared", "-o", os.path.join(obj_dir, "libramxload.so"),
                            os.path.join(obj_dir, "ramx_loader.o"), os.path.join(obj_dir, "ramx_loader_flat.o")])
     return out

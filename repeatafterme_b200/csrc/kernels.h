@@ -17,7 +17,6 @@ struct KernelCfg
   // when the two row states do not fit the register file)
   int maxt[2];      // largest CTA size (threads); caps registers per thread at 65536 / maxt
   extend_fn fn[2];
-  int regs[2];      // filled at init
 };
 
 // MAXT: wide lanes keep the whole 255-register budget (no spills); narrow lanes trade registers
@@ -32,21 +31,19 @@ constexpr int maxt2_for(int C)
 }
 #define RAMCU_CFG(B_, C_, G_)                                                                              \
   {B_, C_, G_, {maxt_for(C_), maxt2_for(C_)},                                                              \
-   {extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1>, extend_kernel<C_, G_, 2 * B_ + 1, maxt2_for(C_), 2>}, \
-   {0, 0}}
+   {extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1>, extend_kernel<C_, G_, 2 * B_ + 1, maxt2_for(C_), 2>}}
 // wide lanes: one pass per CTA only
 #define RAMCU_CFG1(B_, C_, G_) \
-  {B_, C_, G_, {maxt_for(C_), 0}, {extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1>, nullptr}, {0, 0}}
+  {B_, C_, G_, {maxt_for(C_), 0}, {extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1>, nullptr}}
 // same tiling with an explicit (larger) CTA limit: fewer registers per thread, more resident
 // instances -- the capacity fallback for very large families with wide bands
 #define RAMCU_CFG_T(B_, C_, G_, T_) \
-  {B_, C_, G_, {T_, 0}, {extend_kernel<C_, G_, 2 * B_ + 1, T_, 1>, nullptr}, {0, 0}}
+  {B_, C_, G_, {T_, 0}, {extend_kernel<C_, G_, 2 * B_ + 1, T_, 1>, nullptr}}
 #define RAMCU_GEN(C_, G_)                                                                \
   {-1, C_, G_, {maxt_for(C_), maxt2_for(C_)},                                            \
-   {extend_kernel<C_, G_, 0, maxt_for(C_), 1>, extend_kernel<C_, G_, 0, maxt2_for(C_), 2>}, \
-   {0, 0}}
+   {extend_kernel<C_, G_, 0, maxt_for(C_), 1>, extend_kernel<C_, G_, 0, maxt2_for(C_), 2>}}
 #define RAMCU_GEN1(C_, G_) \
-  {-1, C_, G_, {maxt_for(C_), 0}, {extend_kernel<C_, G_, 0, maxt_for(C_), 1>, nullptr}, {0, 0}}
+  {-1, C_, G_, {maxt_for(C_), 0}, {extend_kernel<C_, G_, 0, maxt_for(C_), 1>, nullptr}}
 
 struct CfgList
 {

@@ -185,22 +185,20 @@ extern "C" int ramcu_init(int device, ramcu_ctx **out)
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   collect_cfgs();
-  for (KernelCfg *k : g_cfgs)
-    for (int np = 0; np < 2; ++np)
+  {
+    // Is the image (built for sm_100a only) loadable here? One small kernel answers that; the band
+    // tilings are loaded when a family first needs them (loading all ~100 of them costs 1.7 s, more than
+    // a whole single-family run).
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, (const void *) int32_peak_kernel);
+    if (e != cudaSuccess)
     {
-      if (!k->fn[np])
-        continue;
-      cudaFuncAttributes fa;
-      e = cudaFuncGetAttributes(&fa, (const void *) k->fn[np]);
-      if (e != cudaSuccess)
-      {
-        ramcu_destroy(c);
-        return fail(RAMCU_ERR_CUDA,
-                    "ramcu_init: kernel image not loadable on this device (built for sm_100a): %s",
-                    cudaGetErrorString(e));
-      }
-      k->regs[np] = fa.numRegs;
+      ramcu_destroy(c);
+      return fail(RAMCU_ERR_CUDA,
+                  "ramcu_init: kernel image not loadable on this device (built for sm_100a): %s",
+                  cudaGetErrorString(e));
     }
+  }
   *out = c;
   return RAMCU_OK;
 }

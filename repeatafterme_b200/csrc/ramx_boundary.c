@@ -39,6 +39,7 @@
 
 #include "ramcu.h"
 #include "ramx_loader.h"
+#include "ramx_boundary.h"
 
 /* globals of ram_extend.c that extend_alignment() reads (ram_extend.c:40,52,61) */
 extern int VERBOSE;
@@ -81,11 +82,74 @@ ahead_drop(void)
   memset(&g_ahead, 0, sizeof(g_ahead));
 }
 
+/* Batch front-end (csrc/ramx_batch.c): when set, every extend_alignment() call that is not an -outmat
+ * call is offered to the hook first, with the flattened inputs; it returns 1 after filling the outputs
+ * (or does not return: the recording phase leaves main() with longjmp), 0 to let the call run here. */
+ramx_extend_hook_fn ramx_extend_hook = NULL;
+
 static void
 die(const char *what)
 {
   printf("RAMExtend: CUDA extension failed in %s: %s\n", what, ramcu_last_error());
   exit(1);
+}
+
+/* the right and the left pass share one library upload */
+static void
+ensure_library(struct sequenceLibrary *seqLib)
+{
+  const int timing = getenv("RAMX_TIMING") != NULL;
+  const double t0 = now_s();
+  if (g_lib == NULL || g_lib_seq != seqLib->sequence || g_lib_len != seqLib->length)
+  {
+    ahead_drop();
+    if (g_lib)
+      ramcu_library_free(g_ctx, g_lib);
+    g_lib = NULL;
+    {
+      /* a library built by the product loader travels as the .2bit file's own packed bytes and is
+       * decoded on the device; any other library (1 byte per base) is packed on the device */
+      const struct ramx_twobit_source *src =
+        getenv("RAMCU_BYTE_LIBRARY") ? NULL : ramx_loader_source(seqLib->sequence, seqLib->length);
+      if (src != NULL)
+      {
+        if (ramcu_library_from_twobit(g_ctx, src->blob, src->blob_bytes, src->n_windows,
+                                      (const ramcu_window_t *) src->windows, src->n_nranges, src->n_start,
+                                      src->n_len, src->total, &g_lib) != RAMCU_OK)
+          die("ramcu_library_from_twobit");
+      }
+      else if (ramcu_library_upload(g_ctx, (const uint8_t *) seqLib->sequence, seqLib->length, &g_lib) != RAMCU_OK)
+        die("ramcu_library_upload");
+    }
+    g_lib_seq = seqLib->sequence;
+    g_lib_len = seqLib->length;
+    if (timing)
+      fprintf(stderr, "[ramx timing] library to the device %.3f s\n", now_s() - t0);
+  }
+}
+
+/* forget the library of the previous main() run (its host buffer may have been freed and the address reused) */
+void
+ramx_boundary_forget_library(void)
+{
+  ahead_drop();
+  if (g_lib && g_ctx)
+    ramcu_library_free(g_ctx, g_lib);
+  g_lib = NULL;
+  g_lib_seq = NULL;
+  g_lib_len = 0;
+}
+
+ramcu_ctx *
+ramx_boundary_context(void)
+{
+  if (g_ctx == NULL)
+  {
+    const char *dev = getenv("RAMCU_DEVICE");
+    if (ramcu_init(dev ? atoi(dev) : 0, &g_ctx) != RAMCU_OK)
+      die("ramcu_init");
+  }
+  return g_ctx;
 }
 
 int
@@ -120,43 +184,14 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
 
   const int timing = getenv("RAMX_TIMING") != NULL;
   double t0 = now_s();
+  int handled = 0;
   if (g_ctx == NULL)
   {
-    const char *dev = getenv("RAMCU_DEVICE");
-    if (ramcu_init(dev ? atoi(dev) : 0, &g_ctx) != RAMCU_OK)
-      die("ramcu_init");
+    ramx_boundary_context();
     if (timing)
-      fprintf(stderr, "[ramx timing] CUDA context + kernel images %.3f s\n", now_s() - t0);
+      fprintf(stderr, "[ramx timing] CUDA context %.3f s\n", now_s() - t0);
     t0 = now_s();
   }
-  /* the right and the left pass share one library upload */
-  if (g_lib == NULL || g_lib_seq != seqLib->sequence || g_lib_len != seqLib->length)
-  {
-    ahead_drop();
-    if (g_lib)
-      ramcu_library_free(g_ctx, g_lib);
-    {
-      /* a library built by the product loader travels as the .2bit file's own packed bytes and is
-       * decoded on the device; any other library (1 byte per base) is packed on the device */
-      const struct ramx_twobit_source *src =
-        getenv("RAMCU_BYTE_LIBRARY") ? NULL : ramx_loader_source(seqLib->sequence, seqLib->length);
-      if (src != NULL)
-      {
-        if (ramcu_library_from_twobit(g_ctx, src->blob, src->blob_bytes, src->n_windows,
-                                      (const ramcu_window_t *) src->windows, src->n_nranges, src->n_start,
-                                      src->n_len, src->total, &g_lib) != RAMCU_OK)
-          die("ramcu_library_from_twobit");
-      }
-      else if (ramcu_library_upload(g_ctx, (const uint8_t *) seqLib->sequence, seqLib->length, &g_lib) != RAMCU_OK)
-        die("ramcu_library_upload");
-    }
-    g_lib_seq = seqLib->sequence;
-    g_lib_len = seqLib->length;
-    if (timing)
-      fprintf(stderr, "[ramx timing] library to the device %.3f s\n", now_s() - t0);
-    t0 = now_s();
-  }
-
   /* matrix[cons][A,C,G,T,N]; the soft-masked columns 4..7 must score like N (they do for every
    * matrix score_system.c builds), because the device library keeps 2 bits + an N flag per base */
   memset(&sc, 0, sizeof(sc));
@@ -200,7 +235,17 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
   pr.L = L;
   pr.when_to_stop = WHEN_TO_STOP;
 
-  if (pathStringFile != NULL)
+  if (ramx_extend_hook != NULL && pathStringFile == NULL)
+    handled = ramx_extend_hook(direction ? 1 : 0, n, cores, &sc, &pr, seqLib, cons, ext_len, score_add, &res);
+  if (!handled)
+    ensure_library(seqLib);
+  t0 = now_s();
+
+  if (handled)
+  {
+    /* answered by the batch front-end */
+  }
+  else if (pathStringFile != NULL)
   {
     /* -outmat: the kernel also reports the path state of every band cell of every committed row;
      * the lines of ram_extend.c:1122-1132 are written here, in the reference's order */

@@ -74,6 +74,17 @@ struct range
   int record;                  /* index into the .2bit table */
 };
 
+/* everything the last call allocated (main() never frees; the batch front-end does, through
+ * ramx_loader_release_last(), once a run of main() is over) */
+static struct
+{
+  struct sequenceLibrary *lib;
+  struct coreAlignment *cores;
+  struct range *ranges;
+  char *ranges_text;
+  int n;
+} g_last;
+
 static struct range *
 read_ranges(const char *path, int *n_out)
 {
@@ -139,6 +150,7 @@ read_ranges(const char *path, int *n_out)
     line = nl + 1;
   }
   *n_out = n;
+  g_last.ranges_text = buf;
   return r;   /* names point into buf, which lives as long as the ranges */
 }
 
@@ -330,6 +342,7 @@ decode_window(const struct twobit *t, const struct record *rec, long start, long
  * what the device needs: the windows as packed bytes + N runs (picked up by ramx_boundary.c)
  * ------------------------------------------------------------------------------------------- */
 static struct ramx_twobit_source g_source;
+
 
 const struct ramx_twobit_source *
 ramx_loader_source(const char *sequence, uint64_t length)
@@ -598,6 +611,10 @@ loadSequenceSubsetMinimal(char *twoBitName, char *rangeBEDName, struct coreAlign
   lib->length = total;
   lib->count = n;
 
+  g_last.lib = lib;
+  g_last.cores = cores;
+  g_last.ranges = rg;
+  g_last.n = n;
   g_source.sequence = sequence;
   g_source.total = total;
   g_source.blob = blob;
@@ -617,6 +634,30 @@ loadSequenceSubsetMinimal(char *twoBitName, char *rangeBEDName, struct coreAlign
   }
   /* rg[].name point into the ranges buffer: both stay allocated until exit, like the reference's list */
   return lib;
+}
+
+void
+ramx_loader_release_last(void)
+{
+  if (g_last.lib)
+  {
+    for (int i = 0; i < g_last.n; ++i)
+      free(g_last.lib->identifiers[i]);
+    free(g_last.lib->identifiers);
+    free(g_last.lib->sequence);
+    free(g_last.lib->boundaries);
+    free(g_last.lib->offsets);
+    free(g_last.lib);
+  }
+  free(g_last.cores);
+  free(g_last.ranges);
+  free(g_last.ranges_text);
+  memset(&g_last, 0, sizeof(g_last));
+  free(g_source.blob);
+  free(g_source.windows);
+  free(g_source.n_start);
+  free(g_source.n_len);
+  memset(&g_source, 0, sizeof(g_source));
 }
 
 /* ---------------------------------------------------------------------------------------------

@@ -28,4 +28,8 @@ struct ramx_twobit_source
 /* the source of the library (sequence, length) if the product loader built it, else NULL */
 const struct ramx_twobit_source *ramx_loader_source(const char *sequence, uint64_t length);
 
+/* free everything the last loadSequenceSubsetMinimal() call allocated (batch front-end only: the
+ * reference's main() keeps using the library until it returns) */
+void ramx_loader_release_last(void);
+
 #endif

@@ -20,6 +20,7 @@ def run(binary, tb, rg, tmp, extra=(), env=None):
 
 def main(n=10000, flank=5000, reps=3):
     fam = synth.make_family(4, n, flank, 0.15)
+    print('generated', file=sys.stderr, flush=True)
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
         tb, rg = os.path.join(tmp, "f.2bit"), os.path.join(tmp, "f.tsv")
@@ -27,6 +28,7 @@ def main(n=10000, flank=5000, reps=3):
         env = dict(os.environ, RAMX_TIMING="1")
         walls = []
         for _ in range(reps):
+            print('product run', file=sys.stderr, flush=True)
             w, r = run(os.path.join(ROOT, "repeatafterme_b200", "bin", "RAMExtend"), tb, rg, tmp, env=env)
             assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
             walls.append(w)
@@ -35,7 +37,8 @@ def main(n=10000, flank=5000, reps=3):
         out["product_extended"] = [l for l in r.stdout.splitlines() if l.startswith("Extended")]
         cons = open(os.path.join(tmp, "c.fa")).read()
         ref_bin = os.path.join(ROOT, "oracle", "_ref", "RAMExtend")
-        if os.path.exists(ref_bin):
+        if os.path.exists(ref_bin) and os.environ.get('CLI_BENCH_REFERENCE'):
+            print('reference overhead run', file=sys.stderr, flush=True)
             w, r2 = run(ref_bin, tb, rg, tmp, extra=["-stopafter", "1", "-minimprovement", "100000000"])
             out["reference_host_overhead_wall_s"] = round(w, 3)
         out["consensus_bytes"] = len(cons)
