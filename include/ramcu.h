@@ -25,6 +25,8 @@
  *                        the same call, split into prepare / enqueue / fetch so that many
  *                        independent families (one RAMExtend process each in
  *                        util/extend-stk.pl:365-371) share one context and run concurrently
+ *   ramcu_seed_extend_batch / ramcu_global_align
+ *                        cons_seed_extend() / pair_seed_extend() / global_align()  bnw_extend.c:167-649
  *   ramcu_debug_rows     compute_nw_row() as called by the reference's unit tests
  *                        (bnw_extend.c:1583,1600): forced consensus, band rows returned
  */
@@ -38,7 +40,7 @@ extern "C" {
 
 #define RAMCU_ABI_VERSION 1
 #define RAMCU_NCODES 5            /* matrix columns: A,C,G,T,N (sequence.h:7-15; 99 -> 4)      */
-#define RAMCU_MAX_BANDWIDTH 511   /* 2*B+1 <= 1023 band cells                                  */
+#define RAMCU_MAX_BANDWIDTH 1023  /* 2*B+1 <= 2047 band cells: 32 lanes x 64 cells                */
 
 /* error codes (all negative) */
 #define RAMCU_OK 0
@@ -208,6 +210,39 @@ int ramcu_extend_paths(ramcu_ctx *ctx, ramcu_library *lib, int direction, int n_
                        const ramcu_params_t *params, uint8_t *master_out, int32_t *ext_len_out,
                        int32_t *score_add_out, ramcu_result_t *res, uint8_t *path_state_out,
                        int32_t *row_best_out, int32_t *row_best_idx_out);
+
+/* Seed extension: the other callers of compute_nw_row() (bnw_extend.c:167-649), batched.
+ * One ramcu_seed_t == one cons_seed_extend() call (bnw_extend.h:38-43): the query (host codes 0..3, any
+ * other value is an N base) with its seed [query_seed_start, query_seed_end], the subject seed
+ * [subj_seed_start, subj_seed_end] in library coordinates with the extent of the subject's sequence
+ * (boundaries[] of the reference's seqLib) and its orientation. pair_seed_extend() (bnw_extend.h:31-36)
+ * is the same call with the query taken from the library. Results are the reference's
+ * left_max_score / right_max_score (their sum is the return value before complexity adjustment) and the
+ * glocalSearchResult ranges. n_row[5] = score of an N query base against A,C,G,T,N
+ * (scoreParams->matrix[SYM_N][..]). y_drop as in the reference: negative = no early stop. */
+typedef struct
+{
+  const uint8_t *query;
+  int32_t query_len, query_seed_start, query_seed_end;
+  int32_t orient;
+  int64_t subj_seed_start, subj_seed_end;
+  int64_t lower_seq_bound, upper_seq_bound;
+} ramcu_seed_t;
+typedef struct
+{
+  int32_t left_score, right_score;
+  int32_t query_start, query_end;
+  int64_t subj_start, subj_end;
+  int32_t left_rows, right_rows;   /* rows scanned before the y-drop break */
+} ramcu_seed_result_t;
+int ramcu_seed_extend_batch(ramcu_ctx *ctx, ramcu_library *lib, int n_seeds, const ramcu_seed_t *seeds,
+                            const ramcu_scoring_t *scoring, const int32_t *n_row, int bandwidth, int y_drop,
+                            ramcu_seed_result_t *results);
+/* global_align() (bnw_extend.h:45-49): seq1 (host codes) is the given consensus, seq2 = library
+ * positions [seq2_start, seq2_end]. */
+int ramcu_global_align(ramcu_ctx *ctx, ramcu_library *lib, int orient, const uint8_t *seq1, int seq1_len,
+                       int64_t seq2_start, int64_t seq2_end, const ramcu_scoring_t *scoring, const int32_t *n_row,
+                       int bandwidth, int32_t *global_score, int32_t *local_score, int32_t *local_pos);
 
 /* Test-only second boundary (compute_nw_row, bnw_extend.h:52-58). Runs the extension kernel for
  * `n_rows` rows with the consensus FORCED to forced_cons[r] (NULL = argmax as usual) and returns

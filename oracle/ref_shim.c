@@ -215,3 +215,60 @@ ramref_load(const char *twobit, const char *ranges, int max_flanking_bp, int *n_
   }
   return n;
 }
+
+/* The reference's cons_seed_extend() (bnw_extend.c:196-484) on flat inputs: `name` selects one of the
+ * reference's own scoring systems (lambda / background frequencies included, so the complexity
+ * adjustment is the reference's too). out[7] = return value, query_start, query_end, subj_start,
+ * subj_end, and -- recomputed with adjustment off -- the unadjusted score; n_row_out[5] = the N row. */
+int
+ramref_cons_seed_extend(const char *name, const char *query, int query_len, int query_seed_start,
+                        int query_seed_end, const char *sequence, uint64_t seq_len, const uint64_t *boundaries,
+                        uint64_t subj_seed_start, uint64_t subj_seed_end, int orient, int bandwidth,
+                        int use_complexity_adjust, int y_drop, int64_t *out, int32_t *n_row_out)
+{
+  struct scoringSystem *s = getMatrix((char *) name);
+  struct sequenceLibrary lib;
+  struct glocalSearchResult res;
+  int ****score = allocate_score(1, bandwidth);
+  int nb = 0, sc, i;
+  memset(&lib, 0, sizeof(lib));
+  while (boundaries[nb] != 0)
+    nb++;
+  lib.sequence = (char *) sequence;
+  lib.boundaries = (uint64_t *) boundaries;
+  lib.count = nb;
+  lib.length = seq_len;
+  sc = cons_seed_extend((char *) query, query_len, query_seed_start, query_seed_end, &lib, subj_seed_start,
+                        subj_seed_end, orient, score, s, bandwidth, &res, use_complexity_adjust, y_drop);
+  out[0] = sc;
+  out[1] = res.query_start;
+  out[2] = res.query_end;
+  out[3] = (int64_t) res.subj_start;
+  out[4] = (int64_t) res.subj_end;
+  out[5] = cons_seed_extend((char *) query, query_len, query_seed_start, query_seed_end, &lib, subj_seed_start,
+                            subj_seed_end, orient, score, s, bandwidth, &res, 0, y_drop);
+  for (i = 0; i < 4; i++)
+    n_row_out[i] = s->matrix[SYM_N][i];
+  n_row_out[4] = s->matrix[SYM_N][SYM_N];
+  return sc;
+}
+
+/* The reference's global_align() (bnw_extend.c:486-649); it prints one line to stdout. */
+int
+ramref_global_align(const char *name, int orient, uint64_t seq1_start, uint64_t seq1_end, uint64_t seq2_start,
+                    uint64_t seq2_end, const char *sequence, uint64_t seq_len, int bandwidth)
+{
+  struct scoringSystem *s = getMatrix((char *) name);
+  struct sequenceLibrary lib;
+  uint64_t boundaries[2];
+  int ****score = allocate_score(1, bandwidth);
+  memset(&lib, 0, sizeof(lib));
+  boundaries[0] = seq_len;
+  boundaries[1] = 0;
+  lib.sequence = (char *) sequence;
+  lib.boundaries = boundaries;
+  lib.count = 1;
+  lib.length = seq_len;
+  return global_align(orient, seq1_start, seq1_end, seq1_start, seq2_start, seq2_end, seq2_start, score, 8, &lib, s,
+                      bandwidth);
+}

@@ -36,7 +36,7 @@ ABI_SYMBOLS = (
     "ramcu_device_info", "ramcu_int32_peak", "ramcu_scoring_by_name", "ramcu_library_upload",
     "ramcu_library_from_device", "ramcu_library_from_twobit", "ramcu_library_download", "ramcu_library_free", "ramcu_extend", "ramcu_job_create",
     "ramcu_job_run", "ramcu_job_fetch", "ramcu_job_free", "ramcu_batch_run", "ramcu_debug_rows",
-    "ramcu_job_create_pair", "ramcu_extend_pair", "ramcu_extend_paths",
+    "ramcu_job_create_pair", "ramcu_extend_pair", "ramcu_extend_paths", "ramcu_seed_extend_batch", "ramcu_global_align",
 )
 
 
@@ -103,6 +103,22 @@ def make_params(bandwidth=14, cappenalty=-90, minimprovement=27, L=10000, when_t
     return p
 
 
+class Seed(C.Structure):
+    """ramcu_seed_t: one cons_seed_extend() call (reference bnw_extend.h:38-43)."""
+
+    _fields_ = [("query", C.c_void_p), ("query_len", C.c_int32), ("query_seed_start", C.c_int32),
+                ("query_seed_end", C.c_int32), ("orient", C.c_int32), ("subj_seed_start", C.c_int64),
+                ("subj_seed_end", C.c_int64), ("lower_seq_bound", C.c_int64), ("upper_seq_bound", C.c_int64)]
+
+
+class SeedResult(C.Structure):
+    """ramcu_seed_result_t."""
+
+    _fields_ = [("left_score", C.c_int32), ("right_score", C.c_int32), ("query_start", C.c_int32),
+                ("query_end", C.c_int32), ("subj_start", C.c_int64), ("subj_end", C.c_int64),
+                ("left_rows", C.c_int32), ("right_rows", C.c_int32)]
+
+
 class RamCuError(RuntimeError):
     pass
 
@@ -142,6 +158,8 @@ def load_ramcu(path: str = LIB_PATH) -> C.CDLL:
                                       vp, vp, vp, P(ExtendResult)]
     lib.ramcu_extend_paths.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult),
                                        vp, vp, vp]
+    lib.ramcu_seed_extend_batch.argtypes = [vp, vp, i32, vp, P(Scoring), vp, i32, i32, vp]
+    lib.ramcu_global_align.argtypes = [vp, vp, i32, vp, i32, C.c_int64, C.c_int64, P(Scoring), vp, i32, P(i32), P(i32), P(i32)]
     lib.ramcu_debug_rows.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), i32, vp, vp, vp, vp]
     for name in ABI_SYMBOLS:
         if name not in ("ramcu_last_error", "ramcu_destroy"):
@@ -313,6 +331,38 @@ class RamCu:
 
     def job_free(self, job):
         self._check(self.lib.ramcu_job_free(self.ctx, job))
+
+    # -- seed extension (cons_seed_extend / pair_seed_extend / global_align, bnw_extend.c:167-649) ------
+    def seed_extend_batch(self, lib_h, seeds, scoring: Scoring, n_row, bandwidth: int, y_drop: int = -1):
+        """seeds: list of dicts(query=uint8 codes, query_seed_start, query_seed_end, subj_seed_start,
+        subj_seed_end, lower_seq_bound, upper_seq_bound, orient). Returns a list of SeedResult; the
+        reference's return value before complexity adjustment is left_score + right_score."""
+        n = len(seeds)
+        arr = (Seed * max(n, 1))()
+        keep = []
+        for i, sd in enumerate(seeds):
+            q = np.ascontiguousarray(sd["query"], dtype=np.uint8)
+            keep.append(q)
+            arr[i].query = q.ctypes.data
+            arr[i].query_len = q.size
+            for k in ("query_seed_start", "query_seed_end", "orient", "subj_seed_start", "subj_seed_end",
+                      "lower_seq_bound", "upper_seq_bound"):
+                setattr(arr[i], k, int(sd[k]))
+        res = (SeedResult * max(n, 1))()
+        nr = np.ascontiguousarray(n_row, dtype=np.int32)
+        self._check(self.lib.ramcu_seed_extend_batch(self.ctx, lib_h, n, C.byref(arr), C.byref(scoring), nr.ctypes.data,
+                                                     bandwidth, y_drop, C.byref(res)))
+        return [res[i] for i in range(n)]
+
+    def global_align(self, lib_h, orient: int, seq1, seq2_start: int, seq2_end: int, scoring: Scoring, n_row,
+                     bandwidth: int):
+        q = np.ascontiguousarray(seq1, dtype=np.uint8)
+        nr = np.ascontiguousarray(n_row, dtype=np.int32)
+        g, l, p = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self.lib.ramcu_global_align(self.ctx, lib_h, orient, q.ctypes.data, q.size, seq2_start, seq2_end,
+                                                C.byref(scoring), nr.ctypes.data, bandwidth, C.byref(g), C.byref(l),
+                                                C.byref(p)))
+        return g.value, l.value, p.value
 
     # -- test-only: compute_nw_row boundary -----------------------------------------------------
     def debug_rows(self, lib_h, direction: int, cores: np.ndarray, scoring: Scoring, params: Params,

@@ -79,12 +79,15 @@ struct FamDev
   unsigned char *dbg_path;   // -outmat: [rows][n_ext][W] state of the best path into each cell of the
                              // committed row: 0 substitution, 1 deletion, 2 insertion (bnw_extend.c:1027-1044)
   int *dbg_idx;           // -outmat: [rows][n_ext] band index of the row's first best cell
+  int *seed_rows;         // seed extension: [rows][n_ext][2] = compute_nw_row()'s return value for the given
+                          // consensus base and *max_score_sequence_idx (bnw_extend.c:1020-1024)
   long long *dbg_wait;    // diagnostics: per CTA [0] cycles spent in the grid exchange [1] total cycles
   int n_ext, n_ctas, cta0, B;
   int W, go, ge, cap;
   int minimp, L, stop;
   int mate;               // index of the family's other pass in the same launch (two-pass CTAs), or -1
   int m[8][4];            // m[code][cand]; code 4 = N, 5 = out of bounds (value unused)
+  int mN[8];              // mN[code]: score of an N consensus base (forced consensus 4, seed extension)
 };
 
 __device__ __forceinline__ int imax(int a, int b) { return max(a, b); }
@@ -417,7 +420,7 @@ __device__ __forceinline__ long long global_ns()
 template <int NP>
 struct SharedBlk
 {
-  int4 lut[8];
+  int4 lut[16];   // [code][A,C,G,T | N-consensus,-,-,-]: 32 bytes per base code
   PassShared ps[NP];
   int cta;
 };
@@ -433,7 +436,7 @@ template <int C>
 struct PassRegs
 {
   int Pp[C], Dd[C];             // row state, see the header
-  uint32_t win[(C + 3) / 4];    // base window: byte k = LUT offset (code * 16) of cell k's base
+  uint32_t win[(C + 3) / 4];    // base window: byte k = LUT offset (code * 32) of cell k's base
   uint32_t nib_lo, nib_hi;      // codes of the next band positions entering at the high end
   int maxD;                     // max of Dd over the lane's real cells
   int best[4];                  // row bests of the pending column (instance-wide)
@@ -472,8 +475,11 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   const FamDev *__restrict__ F0 = fams + cta_fam[cta];
   const int cta_in_fam = cta - F0->cta0;
   if (threadIdx.x < 8)
-    sh.lut[threadIdx.x] = make_int4(F0->m[threadIdx.x][0], F0->m[threadIdx.x][1],
-                                    F0->m[threadIdx.x][2], F0->m[threadIdx.x][3]);
+  {
+    sh.lut[2 * threadIdx.x] = make_int4(F0->m[threadIdx.x][0], F0->m[threadIdx.x][1],
+                                        F0->m[threadIdx.x][2], F0->m[threadIdx.x][3]);
+    sh.lut[2 * threadIdx.x + 1] = make_int4(F0->mN[threadIdx.x], 0, 0, 0);
+  }
   __syncthreads();
   const char *lutb = reinterpret_cast<const char *>(sh.lut);
 
@@ -496,7 +502,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
 
   const FamDev *Fp[NP];
   PassRegs<C> ps[NP];
-  bool dbg_on[NP], use_fast[NP], has_forced[NP], has_dbg_best[NP], has_dbg_path[NP];
+  bool dbg_on[NP], use_fast[NP], has_forced[NP], has_dbg_best[NP], has_dbg_path[NP], has_seed_rows[NP];
 
   // ---- set-up of every pass: instance, boundary row, first base window ------------------------
 #pragma unroll
@@ -523,6 +529,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     has_forced[p] = F->forced != nullptr;
     has_dbg_best[p] = F->dbg_best != nullptr;
     has_dbg_path[p] = F->dbg_path != nullptr;
+    has_seed_rows[p] = F->seed_rows != nullptr;
     use_fast[p] = (WS != 0) && gaps_ok && !dbg_on[p];
 #pragma unroll
     for (int i = 0; i < CW; ++i)
@@ -544,7 +551,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     for (int k = 0; k < C; ++k)
     {
       const int code = fetch_code(F->lib2, F->libn, S.start, S.sgn, S.comp, S.tmin, S.tmax, K0 + k - B);
-      const uint32_t b = (uint32_t) (code << 4) << (8 * (k & 3));
+      const uint32_t b = (uint32_t) (code << 5) << (8 * (k & 3));
 #pragma unroll
       for (int i = 0; i < CW; ++i)
         S.win[i] |= (i == (k >> 2)) ? b : 0u;
@@ -579,7 +586,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     PassRegs<C> &S = ps[p];
     const FamDev *__restrict__ F = Fp[p];
     const bool fast = use_fast[p] && (r >= S.r_fast_lo) && (r <= S.r_fast_hi);
-    const bool alldead = !dbg_on[p] && (r >= S.r_dead);   // every cell out of bounds, for good
+    const bool alldead = !dbg_on[p] && !has_seed_rows[p] && (r >= S.r_dead);   // every cell out of bounds, for good
     int best[4] = {kOob, kOob, kOob, kOob};
     if (!alldead)
     {
@@ -787,8 +794,8 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     const int n_ext = F->n_ext;
     if ((r & 15) == 0 && is_last)
       feed16(F->lib2, F->libn, S.start, S.sgn, S.comp, S.tmin, S.tmax, r - B + G * C, S.nib_lo, S.nib_hi);
-    const bool fast = use_fast[p] && (r >= S.r_fast_lo) && (r <= S.r_fast_hi);
-    const bool alldead = !dbg_on[p] && (r >= S.r_dead);
+    const bool fast_row = use_fast[p] && (r >= S.r_fast_lo) && (r <= S.r_fast_hi);
+    const bool alldead = !dbg_on[p] && !has_seed_rows[p] && (r >= S.r_dead);
 
     // argmax over the four bases (ram_extend.c:973-974, 1081-1085)
     int curr = 0, besta = 0;
@@ -803,8 +810,8 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     }
     if (has_forced[p])
     {
-      besta = F->forced[r] & 3;
-      curr = sel4(besta, sums[0], sums[1], sums[2], sums[3]);
+      besta = min((int) F->forced[r], 4);   // 4: an N base of a given query (seed extension)
+      curr = sel4(besta & 3, sums[0], sums[1], sums[2], sums[3]);
     }
     if (has_dbg_best[p])
     {
@@ -821,7 +828,9 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     // commit the chosen base's row (ram_extend.c:1105-1150)
     if (!alldead)
     {
-      const int bestb = sel4(besta, S.best[0], S.best[1], S.best[2], S.best[3]);
+      // an N base of a given query is not one of the four candidates of the sweep: its row takes the exact path
+      const bool fast = fast_row && (besta < 4);
+      int bestb = sel4(besta, S.best[0], S.best[1], S.best[2], S.best[3]);
       int idx = kBig;
       if (fast)
       {
@@ -922,6 +931,13 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         const int agg = exact_pass<C, false, false>(S.Pp, S.Dd, S.win, lutb, besta, go, ge, (gl == 0) ? kNeg : kNegInf,
                                                     gl, W, B, r, S.tmin, S.tmax, nob, 0, noi, h0, nodbg);
         const int hin = carry_scan_exact<C, G>(agg, open, ge, gl);
+        if (besta == 4)
+        {
+          int b = kNeg;
+          exact_pass<C, true, false>(S.Pp, S.Dd, S.win, lutb, besta, go, ge, hin, gl, W, B, r, S.tmin, S.tmax, b, 0, noi,
+                                     h0, nodbg);
+          bestb = group_max<G>(b, gl, lane);
+        }
         exact_pass<C, true, true>(S.Pp, S.Dd, S.win, lutb, besta, go, ge, hin, gl, W, B, r, S.tmin, S.tmax, nob, bestb,
                                   idx, h0, dbg);
         S.Dd[C - 1] = (G > 1) ? __shfl_down_sync(kFull, h0, 1) : kNeg;
@@ -944,6 +960,11 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       }
       if (has_dbg_path[p] && S.valid && gl == 0)
         F->dbg_idx[(size_t) r * n_ext + S.inst] = kidx;
+      if (has_seed_rows[p] && S.valid && gl == 0)
+      {
+        F->seed_rows[((size_t) r * n_ext + S.inst) * 2] = bestb;
+        F->seed_rows[((size_t) r * n_ext + S.inst) * 2 + 1] = r - B + kidx;
+      }
     }
 
     // improvement / stop rule (ram_extend.c:1194-1223)
@@ -966,7 +987,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     if (S.active)
     {
       // slide the base window by one band position
-      uint32_t in = (S.nib_lo << 4) & 0xf0u;
+      uint32_t in = (S.nib_lo << 5) & 0x1e0u;
       S.nib_lo = __funnelshift_r(S.nib_lo, S.nib_hi, 4);
       S.nib_hi >>= 4;
       if (G > 1)

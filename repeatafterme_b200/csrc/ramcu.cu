@@ -132,6 +132,7 @@ struct ramcu_job
   int *d_dbg_rows = nullptr, *d_dbg_best = nullptr, *d_dbg_sums = nullptr;
   unsigned char *d_dbg_path = nullptr;   // -outmat mode (negative dbg_rows in job_create_impl)
   int *d_dbg_idx = nullptr;
+  int *d_seed_rows = nullptr;   // seed extension: [L][n_ext][2]
   long long *d_dbg_wait = nullptr;   // RAMCU_STATS=1 diagnostics
   const KernelCfg *ran_cfg = nullptr;
   int stats_ctas = 0;
@@ -671,7 +672,7 @@ static void pinned_put(ramcu_ctx *c, void *p, size_t cap)
 static void free_job_device(ramcu_ctx *c, ramcu_job *j)
 {
   void *ptrs[] = {j->d_inst, j->d_out, j->d_slots, j->d_fam, j->d_cta_fam, j->d_forced, j->d_dbg_rows,
-                  j->d_dbg_best, j->d_dbg_sums, j->d_dbg_wait, j->d_dbg_path, j->d_dbg_idx};
+                  j->d_dbg_best, j->d_dbg_sums, j->d_dbg_wait, j->d_dbg_path, j->d_dbg_idx, j->d_seed_rows};
   for (void *p : ptrs)
     if (p)
     {
@@ -713,7 +714,7 @@ static void destroy_job(ramcu_ctx *c, ramcu_job *j)
 static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
                            const ramcu_core_t *cores, const ramcu_scoring_t *sc,
                            const ramcu_params_t *pr, int dbg_rows, const uint8_t *forced,
-                           ramcu_job **out)
+                           ramcu_job **out, const int32_t *n_row = nullptr)
 {
   if (!c || !lib || !sc || !pr || !out || (n_cores > 0 && !cores))
     return fail(RAMCU_ERR_ARG, "ramcu_job_create: NULL argument");
@@ -796,6 +797,12 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
       CKJ(cudaMallocAsync(&j->d_dbg_best, rows * j->n_ext * 4 * sizeof(int), c->stream));
       CKJ(cudaMallocAsync(&j->d_dbg_sums, rows * 4 * sizeof(int), c->stream));
     }
+    if (dbg_rows == 0 && forced)   // seed extension: the query is the consensus, row values come back
+    {
+      CKJ(cudaMallocAsync(&j->d_forced, std::max(pr->L, 1), c->stream));
+      CKJ(cudaMemcpyAsync(j->d_forced, forced, pr->L, cudaMemcpyHostToDevice, c->stream));
+      CKJ(cudaMallocAsync(&j->d_seed_rows, (size_t) std::max(pr->L, 1) * j->n_ext * 2 * sizeof(int), c->stream));
+    }
     if (dbg_rows > 0)
     {
       CKJ(cudaMallocAsync(&j->d_dbg_rows, (size_t) dbg_rows * j->n_ext * W * 2 * sizeof(int), c->stream));
@@ -832,6 +839,10 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     f.dbg_idx = j->d_dbg_idx;
     f.dbg_best = j->d_dbg_best;
     f.dbg_sums = j->d_dbg_sums;
+    f.seed_rows = j->d_seed_rows;
+    if (n_row)
+      for (int code = 0; code < RAMCU_NCODES; ++code)
+        f.mN[code] = n_row[code];
     // pageable source: the copy is staged before the call returns, `f` and `inst` may go away
     CKJ(cudaMemcpyAsync(j->d_fam, &f, sizeof(f), cudaMemcpyHostToDevice, c->stream));
   }
@@ -1302,6 +1313,201 @@ extern "C" int ramcu_extend_pair(ramcu_ctx *c, ramcu_library *lib, int n_cores, 
   ramcu_job_free(c, jobs[0]);
   ramcu_job_free(c, jobs[1]);
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// seed extension: the other callers of compute_nw_row() (bnw_extend.c:167-649)
+// ------------------------------------------------------------------------------------------
+// cons_seed_extend() runs the band row with a GIVEN consensus -- the query -- against one subject
+// sequence, left of the seed and right of it, and keeps the best row score and where it was reached.
+// Here every extension is a one-instance family with a forced consensus (the column sums play no
+// role): 2 x n of them share one ramcu_batch_run, the kernel returns compute_nw_row()'s value and
+// sequence index for every row, and the reference's scan over the rows (running maximum, y-drop
+// break: bnw_extend.c:338-367, 404-440) is applied to those values here.
+static void seed_scan(const int *rows, int n_rows, int y_drop, bool right, int *max_score, int *seq_idx,
+                      int *cons_idx, int *rows_used)
+{
+  int best = 0, sidx = -1, cidx = -1, r = 0;
+  for (r = 0; r < n_rows; ++r)
+  {
+    const int sc = rows[2 * r], pos = rows[2 * r + 1];
+    // the reference's right extension compares with the literal 180 whatever y_drop is (bnw_extend.c:429)
+    if (y_drop >= 0 && best - sc > (right ? 180 : y_drop))
+      break;
+    if (sc > best)
+    {
+      best = sc;
+      sidx = pos;
+      cidx = r;
+    }
+  }
+  *max_score = best;
+  *seq_idx = sidx;
+  *cons_idx = cidx;
+  *rows_used = r;
+}
+
+extern "C" int ramcu_seed_extend_batch(ramcu_ctx *c, ramcu_library *lib, int n, const ramcu_seed_t *seeds,
+                                       const ramcu_scoring_t *sc, const int32_t *n_row, int bandwidth, int y_drop,
+                                       ramcu_seed_result_t *results)
+{
+  if (!c || !lib || !sc || !n_row || (n > 0 && (!seeds || !results)) || n < 0)
+    return fail(RAMCU_ERR_ARG, "ramcu_seed_extend_batch: invalid argument");
+  CK(cudaSetDevice(c->device));
+  std::vector<ramcu_job *> jobs((size_t) 2 * n, nullptr);
+  auto cleanup = [&]() {
+    for (ramcu_job *j : jobs)
+      if (j)
+        destroy_job(c, j);
+  };
+  std::vector<uint8_t> forced;
+  for (int i = 0; i < n; ++i)
+  {
+    const ramcu_seed_t &s = seeds[i];
+    if (!s.query || s.query_len < 0 || s.query_seed_start < 0 || s.query_seed_end < s.query_seed_start ||
+        s.query_seed_end >= s.query_len)
+    {
+      cleanup();
+      return fail(RAMCU_ERR_ARG, "ramcu_seed_extend_batch: seed %d: query seed outside the query", i);
+    }
+    for (int side = 0; side < 2; ++side)   // 0 = left (direction 0), 1 = right (direction 1)
+    {
+      const int rows = side ? s.query_len - (s.query_seed_end + 1) : s.query_seed_start;
+      if (rows <= 0)
+        continue;
+      forced.resize(rows);
+      for (int r = 0; r < rows; ++r)
+      {
+        const uint8_t b = side ? s.query[s.query_seed_end + r + 1] : s.query[s.query_seed_start - r - 1];
+        forced[r] = b > 3 ? 4 : b;
+      }
+      ramcu_core_t core;
+      memset(&core, 0, sizeof(core));
+      core.orient = s.orient ? 1 : 0;
+      core.left_extendable = core.right_extendable = 1;
+      core.left_seq_pos = s.orient ? s.subj_seed_end : s.subj_seed_start;     // bnw_extend.c:307-313
+      core.right_seq_pos = s.orient ? s.subj_seed_start : s.subj_seed_end;
+      // the seed itself is out of bounds for both extensions (bnw_extend.c:326-332, 386-391)
+      const bool low_side = (side == 0) != (s.orient != 0);
+      core.lower_seq_bound = low_side ? s.lower_seq_bound : s.subj_seed_end + 1;
+      core.upper_seq_bound = low_side ? s.subj_seed_start - 1 : s.upper_seq_bound;
+      ramcu_params_t pr;
+      memset(&pr, 0, sizeof(pr));
+      pr.bandwidth = bandwidth;
+      pr.L = rows;
+      pr.when_to_stop = 1 << 30;
+      int rc = job_create_impl(c, lib, side, 1, &core, sc, &pr, 0, forced.data(), &jobs[2 * i + side], n_row);
+      if (rc)
+      {
+        cleanup();
+        return rc;
+      }
+    }
+  }
+  std::vector<ramcu_job *> run;
+  for (ramcu_job *j : jobs)
+    if (j && j->n_ctas > 0)
+      run.push_back(j);
+  if (!run.empty())
+  {
+    int rc = ramcu_batch_run(c, (int) run.size(), run.data());
+    if (rc)
+    {
+      cleanup();
+      return rc;
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess)
+    {
+      cleanup();
+      return fail(RAMCU_ERR_CUDA, "seed extension kernel failed: %s", cudaGetErrorString(e));
+    }
+  }
+  std::vector<int> rows_host;
+  for (int i = 0; i < n; ++i)
+  {
+    const ramcu_seed_t &s = seeds[i];
+    int score[2] = {0, 0}, seq_idx[2] = {-1, -1}, cons_idx[2] = {-1, -1}, used[2] = {0, 0};
+    for (int side = 0; side < 2; ++side)
+    {
+      ramcu_job *j = jobs[2 * i + side];
+      if (!j || j->n_ctas == 0)
+        continue;
+      rows_host.resize((size_t) 2 * j->pr.L);
+      cudaError_t e = cudaMemcpy(rows_host.data(), j->d_seed_rows, rows_host.size() * sizeof(int), cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess)
+      {
+        cleanup();
+        return fail(RAMCU_ERR_CUDA, "ramcu_seed_extend_batch: %s", cudaGetErrorString(e));
+      }
+      seed_scan(rows_host.data(), j->pr.L, y_drop, side == 1, &score[side], &seq_idx[side], &cons_idx[side], &used[side]);
+    }
+    ramcu_seed_result_t &o = results[i];
+    o.left_score = score[0];
+    o.right_score = score[1];
+    o.left_rows = used[0];
+    o.right_rows = used[1];
+    o.query_start = s.query_seed_start - (cons_idx[0] + 1);
+    o.query_end = s.query_seed_end + (cons_idx[1] + 1);
+    // bnw_extend.c:444-449
+    o.subj_start = s.subj_seed_start - ((s.orient ? seq_idx[1] : seq_idx[0]) + 1);
+    o.subj_end = s.subj_seed_end + ((s.orient ? seq_idx[0] : seq_idx[1]) + 1);
+  }
+  cleanup();
+  return RAMCU_OK;
+}
+
+// global_align() (bnw_extend.c:486-649): one right extension of seq2 with seq1 as the given consensus, from
+// the top-left corner of the band to its last row; the global score is the best cell of the last row
+// (never below 0), the local score the best row value and where it was reached.
+extern "C" int ramcu_global_align(ramcu_ctx *c, ramcu_library *lib, int orient, const uint8_t *seq1, int seq1_len,
+                                  int64_t seq2_start, int64_t seq2_end, const ramcu_scoring_t *sc,
+                                  const int32_t *n_row, int bandwidth, int32_t *global_score, int32_t *local_score,
+                                  int32_t *local_pos)
+{
+  if (!c || !lib || !sc || !n_row || !seq1 || seq1_len <= 0 || !global_score)
+    return fail(RAMCU_ERR_ARG, "ramcu_global_align: invalid argument");
+  CK(cudaSetDevice(c->device));
+  std::vector<uint8_t> forced(seq1_len);
+  for (int r = 0; r < seq1_len; ++r)
+    forced[r] = seq1[r] > 3 ? 4 : seq1[r];
+  ramcu_core_t core;
+  memset(&core, 0, sizeof(core));
+  core.orient = orient ? 1 : 0;
+  core.left_extendable = 0;
+  core.right_extendable = 1;
+  core.left_seq_pos = core.right_seq_pos = seq2_start - 1;   // bnw_extend.c:601-607
+  core.lower_seq_bound = seq2_start;
+  core.upper_seq_bound = seq2_end + 1;
+  ramcu_params_t pr;
+  memset(&pr, 0, sizeof(pr));
+  pr.bandwidth = bandwidth;
+  pr.L = seq1_len;
+  pr.when_to_stop = 1 << 30;
+  ramcu_job *j = nullptr;
+  int rc = job_create_impl(c, lib, 1, 1, &core, sc, &pr, 0, forced.data(), &j, n_row);
+  if (rc)
+    return rc;
+  rc = ramcu_job_run(c, j);
+  std::vector<int> rows((size_t) 2 * seq1_len);
+  if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess)
+    rc = fail(RAMCU_ERR_CUDA, "ramcu_global_align: kernel failed");
+  if (!rc && cudaMemcpy(rows.data(), j->d_seed_rows, rows.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = fail(RAMCU_ERR_CUDA, "ramcu_global_align: copy failed");
+  destroy_job(c, j);
+  if (rc)
+    return rc;
+  int best = 0, pos = -1;
+  for (int r = 0; r < seq1_len; ++r)
+    if (rows[2 * r] > best)
+    {
+      best = rows[2 * r];
+      pos = rows[2 * r + 1];
+    }
+  *global_score = std::max(0, rows[2 * (seq1_len - 1)]);
+  if (local_score) *local_score = best;
+  if (local_pos) *local_pos = pos;
+  return RAMCU_OK;
 }
 
 // ------------------------------------------------------------------------------------------

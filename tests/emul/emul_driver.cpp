@@ -390,3 +390,68 @@ extern "C" int emul_extend_pair(int C, int G, int WS, int threads, const uint8_t
   }
   return 0;
 }
+
+// One seed-extension pass (ramcu_seed_extend_batch's unit of work, ramcu.cu): a one-instance family with a
+// given consensus (values 0..3, 4 = N) of `rows` rows; returns compute_nw_row()'s value and sequence index
+// per row (FamDev::seed_rows).
+extern "C" int emul_seed_rows(int C, int G, int WS, const uint8_t *seq, uint64_t seq_len, int direction,
+                              const ramcu_core_t *core, const ramcu_scoring_t *sc, const int32_t *n_row, int bandwidth,
+                              int rows, const uint8_t *forced, int32_t *rows_out)
+{
+  const Cfg *cfg = nullptr;
+  for (const Cfg &c : kCfgs)
+    if (c.C == C && c.G == G && c.WS == WS)
+      cfg = &c;
+  const int W = 2 * bandwidth + 1;
+  if (!cfg || (WS && WS != W) || C * G < W)
+    return -2;
+  const unsigned long long n_chunks = (seq_len + 31) / 32;
+  std::vector<uint32_t> a2(n_chunks * 2 + 8, 0), an(n_chunks + 8, 0xffffffffu);
+  {
+    LaunchArgs p = {};
+    p.pfn = pack_library_kernel;
+    p.bytes = seq;
+    p.len = seq_len;
+    p.n_chunks = n_chunks;
+    p.lib2 = a2.data() + 4;
+    p.libn = an.data() + 4;
+    if (launch(p, 2, 32))
+      return -1;
+  }
+  std::vector<InstDev> inst;
+  flatten_cores(direction ? 1 : 0, 1, core, seq_len, inst);
+  if (inst.size() != 1 || rows <= 0)
+    return -3;
+  ramcu_params_t pr;
+  memset(&pr, 0, sizeof(pr));
+  pr.bandwidth = bandwidth;
+  pr.L = rows;
+  pr.when_to_stop = 1 << 30;
+  std::vector<int> thigh(1), tpos(1), result(8, 0), cta_fam(1, 0), srows((size_t) 2 * rows, 0);
+  std::vector<unsigned char> master(rows + 1);
+  std::vector<unsigned long long> slots((size_t) (rows + 1) * 4 * kRedStride, 0);
+  FamDev f;
+  fill_family(f, sc, &pr, 1, 1);
+  for (int code = 0; code < RAMCU_NCODES; ++code)
+    f.mN[code] = n_row[code];
+  f.lib2 = a2.data() + 4;
+  f.libn = an.data() + 4;
+  f.inst = inst.data();
+  f.master = master.data();
+  f.thigh = thigh.data();
+  f.tpos = tpos.data();
+  f.result = result.data();
+  f.slots = slots.data();
+  f.forced = forced;
+  f.seed_rows = srows.data();
+  int ticket = 0;
+  LaunchArgs a = {};
+  a.fn = cfg->fn;
+  a.fams = &f;
+  a.cta_fam = cta_fam.data();
+  a.ticket = &ticket;
+  if (launch(a, 1, 32))
+    return -1;
+  memcpy(rows_out, srows.data(), srows.size() * sizeof(int));
+  return 0;
+}

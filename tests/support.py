@@ -114,6 +114,10 @@ class Reference:
         lib.ramref_extend.argtypes = [i32, i32, vp, vp, u64, vp, i32, i32, i32, i32, i32, i32, i32, i32,
                                       vp, vp, vp, P(C.c_double)]
         lib.ramref_nw_row.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, P(i32)]
+        i64 = C.c_int64
+        lib.ramref_cons_seed_extend.argtypes = [C.c_char_p, vp, i32, i32, i32, vp, u64, vp, u64, u64, i32, i32, i32, i32,
+                                                vp, vp]
+        lib.ramref_global_align.argtypes = [C.c_char_p, i32, u64, u64, u64, u64, vp, u64, i32]
         lib.ramref_load.argtypes = [C.c_char_p, C.c_char_p, i32, P(i32), P(u64), vp, vp, vp, vp]
 
     def scoring(self, name, rs=(1, -1, -5)) -> OracleScoring:
@@ -157,6 +161,26 @@ class Reference:
         rows = int((master != 100).sum())   # the shim pre-fills master[] with 100
         return dict(extended_bp=bp, rows_processed=rows, master=master, ext_len=ext_len,
                     score_add=score_add, seconds=secs.value)
+
+    def cons_seed_extend(self, name, query, q_seed_start, q_seed_end, seq, boundaries, s_seed_start, s_seed_end,
+                         orient, bandwidth, adjust=0, y_drop=-1):
+        """the reference's cons_seed_extend() object code -> dict(score, query_start, query_end, subj_start,
+        subj_end, unadjusted, n_row)"""
+        query = np.ascontiguousarray(query, dtype=np.uint8)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        b = np.ascontiguousarray(list(boundaries) + [0], dtype=np.uint64)
+        out = np.zeros(7, dtype=np.int64)
+        nrow = np.zeros(5, dtype=np.int32)
+        self.lib.ramref_cons_seed_extend(name.encode(), query.ctypes.data, query.size, q_seed_start, q_seed_end,
+                                         seq.ctypes.data, seq.size, b.ctypes.data, s_seed_start, s_seed_end, orient,
+                                         bandwidth, adjust, y_drop, out.ctypes.data, nrow.ctypes.data)
+        return dict(score=int(out[0]), query_start=int(out[1]), query_end=int(out[2]), subj_start=int(out[3]),
+                    subj_end=int(out[4]), unadjusted=int(out[5]), n_row=nrow)
+
+    def global_align(self, name, orient, seq1_start, seq1_end, seq2_start, seq2_end, seq, bandwidth):
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        return self.lib.ramref_global_align(name.encode(), orient, seq1_start, seq1_end, seq2_start, seq2_end,
+                                            seq.ctypes.data, seq.size, bandwidth)
 
     def load(self, twobit, ranges, max_flanking_bp):
         n, slen = i32(), u64()

@@ -86,3 +86,22 @@ def test_wide_bands_equal_reference(ramcu, key):
             _check(case["want"][d], _got(*o), f"{key} pair dir={d}")
     finally:
         ramcu.free_library(lib)
+
+
+def test_bandwidth_1000_vs_oracle(ramcu, oracle):
+    """the widest band the register tilings take (2 x 1023 + 1 cells on 32 lanes x 64 cells): bandwidth 1000
+    and 1023 against the oracle"""
+    from repeatafterme_b200 import synth
+    from tests import support
+    fam = synth.make_family(71, 24, 350, 0.15, pad=30, one_sided_frac=0.2)
+    osc = oracle.scoring("18p43g")
+    lib = ramcu.upload_library(fam.sequence)
+    try:
+        for B in (1000, 1023):
+            p = make_params(bandwidth=B, minimprovement=27, L=20000)
+            for d in (1, 0):
+                want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+                got = _got(*ramcu.extend(lib, d, fam.cores, osc.to_product(), p))
+                support.compare_extend(want, got, f"B={B} dir={d}")
+    finally:
+        ramcu.free_library(lib)
