@@ -461,6 +461,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   constexpr int HW = (C + 31) / 32;
   // static band: index of the last real cell inside the last lane
   constexpr int kR = WS ? WS - 1 - (G - 1) * C : C - 1;
+  constexpr bool kExtras = (NP == 1);
 
   RAMCU_SHARED_STRUCT(SharedBlk<NP>, sh);
 
@@ -525,11 +526,13 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     S.comp = I.comp;
     S.tmin = I.tmin;
     S.tmax = I.tmax;
-    dbg_on[p] = (F->dbg_rows != nullptr) || (F->dbg_path != nullptr);
-    has_forced[p] = F->forced != nullptr;
-    has_dbg_best[p] = F->dbg_best != nullptr;
-    has_dbg_path[p] = F->dbg_path != nullptr;
-    has_seed_rows[p] = F->seed_rows != nullptr;
+    // forced consensus, debug rows, -outmat states and per-row seed values exist for single passes only
+    // (ramcu_job_create_pair never asks for them): the two-pass kernel carries none of that code
+    dbg_on[p] = kExtras && ((F->dbg_rows != nullptr) || (F->dbg_path != nullptr));
+    has_forced[p] = kExtras && F->forced != nullptr;
+    has_dbg_best[p] = kExtras && F->dbg_best != nullptr;
+    has_dbg_path[p] = kExtras && F->dbg_path != nullptr;
+    has_seed_rows[p] = kExtras && F->seed_rows != nullptr;
     use_fast[p] = (WS != 0) && gaps_ok && !dbg_on[p];
 #pragma unroll
     for (int i = 0; i < CW; ++i)
@@ -550,7 +553,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
 #pragma unroll 1
     for (int k = 0; k < C; ++k)
     {
-      const int code = fetch_code(F->lib2, F->libn, S.start, S.sgn, S.comp, S.tmin, S.tmax, K0 + k - B);
+      const int code = fetch_code(F->lib2, F->libn, I.start, I.sgn, I.comp, S.tmin, S.tmax, K0 + k - B);
       const uint32_t b = (uint32_t) (code << 5) << (8 * (k & 3));
 #pragma unroll
       for (int i = 0; i < CW; ++i)
@@ -574,7 +577,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   }
 
 #ifndef RAMCU_EMUL
-  const bool stats = (F0->dbg_wait != nullptr);
+  const bool stats = kExtras && (F0->dbg_wait != nullptr);   // RAMCU_STATS diagnostics: single passes only
   const long long t_begin = stats ? clock64() : 0;
   long long t_wait = 0;
 #endif

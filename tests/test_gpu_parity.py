@@ -137,7 +137,7 @@ def test_edge_cases(ramcu, oracle):
                 got = _got(*ramcu.extend(lib, d, cs, sc, p))
                 support.compare_extend(want, got, f"edge {kw} n={cs.size} dir={d}")
         with pytest.raises(RamCuError):
-            ramcu.extend(lib, 1, fam.cores, sc, make_params(bandwidth=600))
+            ramcu.extend(lib, 1, fam.cores, sc, make_params(bandwidth=1024))
     finally:
         ramcu.free_library(lib)
 
