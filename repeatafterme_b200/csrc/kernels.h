@@ -21,13 +21,23 @@ struct KernelCfg
 
 // MAXT: wide lanes keep the whole 255-register budget (no spills); narrow lanes trade registers
 // for more resident warps. Two passes per thread hold two row states.
+// Lanes of 21..41 cells, one pass: 170 registers (12 resident warps per SM) rather than 255 (8). In a crowded
+// batch that is worth 9 % (config-5 mix: 1616 against 1486 GCUPS); a family alone on the device loses 8 %
+// (two single-pass launches of config 4: 25.4 against 23.4 ms) -- but a family alone runs both passes in
+// the same threads (the two-pass variants keep 255 registers).
+#ifndef RAMCU_MAXT1_WIDE
+#define RAMCU_MAXT1_WIDE 384
+#endif
 constexpr int maxt_for(int C)
 {
-  return C <= 8 ? 768 : C <= 13 ? 512 : C <= 20 ? 384 : 256;
+  return C <= 8 ? 768 : C <= 13 ? 512 : C <= 20 ? 384 : C <= 41 ? RAMCU_MAXT1_WIDE : 256;
 }
+#ifndef RAMCU_MAXT2_MID
+#define RAMCU_MAXT2_MID 19
+#endif
 constexpr int maxt2_for(int C)
 {
-  return C <= 6 ? 768 : C <= 11 ? 512 : C <= 19 ? 384 : 256;
+  return C <= 6 ? 768 : C <= 11 ? 512 : C <= RAMCU_MAXT2_MID ? 384 : 256;
 }
 #define RAMCU_CFG(B_, C_, G_)                                                                              \
   {B_, C_, G_, {maxt_for(C_), maxt2_for(C_)},                                                              \

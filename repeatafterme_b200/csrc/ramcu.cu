@@ -1118,12 +1118,19 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
     jobs[i]->timed_gen = 0;
     jobs[i]->in_batch = true;
   }
+  // A crowded device hides every family's column exchange behind other families' rows: there the
+  // single-pass tilings with the fewest lanes per instance win (measured on the config-5 mix: 1485 against
+  // 1297 GCUPS with two passes per thread). Two passes per thread are for a device that is not full.
+  long long batch_instances = 0;
+  for (int i = 0; i < n_jobs; ++i)
+    batch_instances += jobs[i]->n_ext;
+  const bool crowded = batch_instances >= (long long) c->sm_count * 256 && !getenv("RAMCU_PAIR_ALWAYS");
   for (int i = 0; i < n_jobs; ++i)
   {
     ramcu_job *j = jobs[i];
     if (j->n_ctas == 0 || !j->in_batch)
       continue;
-    ramcu_job *m = j->mate;
+    ramcu_job *m = crowded ? nullptr : j->mate;
     if (m && m->in_batch && m->n_ctas > 0 && j->pair_cfg && j->pair_batch_ctas > 0)
     {
       ramcu_job *a = j->direction ? j : m, *b = j->direction ? m : j;
@@ -1275,7 +1282,7 @@ extern "C" int ramcu_job_create_pair(ramcu_ctx *c, ramcu_library *lib, int n_cor
     return rc;
   }
   ramcu_job *a = *right, *b = *left;
-  if (a->n_ctas > 0 && b->n_ctas > 0)
+  if (a->n_ctas > 0 && b->n_ctas > 0 && !getenv("RAMCU_NO_PAIR"))   // RAMCU_NO_PAIR: tuning aid
   {
     Plan solo;
     int nb = 0;
