@@ -333,8 +333,9 @@ def run_cuda(args):
     lib = rc.upload_library(host_seq.numpy())
     # Right and left pass share one launch (ramcu_job_create_pair): every instance of the synthetic
     # family is its own sequence, so the overlap-avoidance step main() runs between the passes
-    # (ram_extend.c:445-499) cannot change a bound and the left pass reads the same cores. Checked
-    # below against two separate ramcu_extend calls. --sequential times the two-launch form.
+    # (ram_extend.c:445-499) cannot change a bound and the left pass reads the same cores. The planner
+    # decides between two single-pass layouts side by side and both passes in the same threads. Checked
+    # below against the reference golden. --sequential times the two-launch form.
     if args.sequential:
         jobs = [rc.job_create(lib, d, fam.cores, sc, p) for d in (1, 0)]
     else:
@@ -373,6 +374,7 @@ def run_cuda(args):
     outs = [rc.job_fetch(j, fam.cores.size, p.L) for j in jobs]
     cu_step = sum(o[0].rows_processed * o[0].n_extendable * (2 * p.bandwidth + 1) * 4.0 for o in outs)
     lanes = outs[0][0].lanes_per_instance
+    passes_per_thread = outs[0][0].passes_per_thread
     bp = (outs[0][0].extended_bp, outs[1][0].extended_bp)
     # the timed job's outputs against the reference: rank 0's family is the one whose reference outputs are
     # committed (tests/golden/full_config4.npz: the reference's extend_alignment() object code on exactly
@@ -548,8 +550,12 @@ def run_cuda(args):
             "data": "synthetic", "config": dict(workload_config(world), instances=n, flank_bp=flank),
             "details": {"lanes_per_instance": lanes, "extended_bp": list(bp), "parity": checked,
                         "passes": "two launches, right then left" if args.sequential else
-                                  "right and left pass of the family in the same threads, taking turns row by row "
-                                  "(independent here: every instance is its own sequence)",
+                                  ("right and left pass of the family in ONE launch (independent here: every instance is "
+                                   "its own sequence): " +
+                                   ("both passes in the same threads, taking turns row by row" if passes_per_thread == 2 else
+                                    "each pass on its own CTAs with the layout it would have alone, the two sets of CTAs "
+                                    "co-resident, so one pass computes while the other's column sums travel")),
+                        "passes_per_thread": passes_per_thread,
                         "timing": "CUDA events on the launching stream around each step, L2 flushed between steps "
                                   "(256 MiB write), max over ranks"},
             "families_per_s": round(world * args.steps / (dev_ms * 1e-3), 2),

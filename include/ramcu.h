@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define RAMCU_ABI_VERSION 1
+#define RAMCU_ABI_VERSION 2
 #define RAMCU_NCODES 5            /* matrix columns: A,C,G,T,N (sequence.h:7-15; 99 -> 4)      */
 #define RAMCU_MAX_BANDWIDTH 1023  /* 2*B+1 <= 2047 band cells: 32 lanes x 64 cells                */
 
@@ -100,6 +100,8 @@ typedef struct
   int32_t n_extendable;    /* instances extendable in this direction                          */
   float kernel_ms;         /* device time of the extension kernels (CUDA events), if measured  */
   int32_t lanes_per_instance; /* configuration the launch used                                */
+  int32_t passes_per_thread;  /* 2: the family's right and left pass ran in the same threads; 1: one pass per
+                               * thread (on its own, or next to the other pass's CTAs in the same launch)    */
 } ramcu_result_t;
 
 const char *ramcu_last_error(void);

@@ -86,6 +86,7 @@ class ExtendResult(C.Structure):
         ("n_extendable", C.c_int32),
         ("kernel_ms", C.c_float),
         ("lanes_per_instance", C.c_int32),
+        ("passes_per_thread", C.c_int32),
     ]
 
     def as_dict(self) -> dict:

@@ -449,7 +449,11 @@ struct PassRegs
   bool valid, active;
 };
 
-template <int C, int G, int WS, int MAXT, int NP>
+// EX: the instantiation also carries the code of the diagnostic and per-row outputs (forced consensus, debug
+// rows, -outmat path states, per-row seed values, verbose dumps, RAMCU_STATS). The lean instantiations
+// (EX = false) are what plain extensions run: none of that code, fewer registers (e.g. <27,3,81,384,1>: 136
+// instead of 204 bytes of spill stores).
+template <int C, int G, int WS, int MAXT, int NP, bool EX>
 __global__ void __launch_bounds__(MAXT, 1)
 extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, int *ticket)
 {
@@ -461,7 +465,8 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   constexpr int HW = (C + 31) / 32;
   // static band: index of the last real cell inside the last lane
   constexpr int kR = WS ? WS - 1 - (G - 1) * C : C - 1;
-  constexpr bool kExtras = (NP == 1);
+  static_assert(!EX || NP == 1, "diagnostic outputs exist for single passes only");
+  constexpr bool kExtras = EX;
 
   RAMCU_SHARED_STRUCT(SharedBlk<NP>, sh);
 

@@ -17,6 +17,9 @@ struct KernelCfg
   // when the two row states do not fit the register file)
   int maxt[2];      // largest CTA size (threads); caps registers per thread at 65536 / maxt
   extend_fn fn[2];
+  // single pass with the diagnostic / per-row outputs compiled in (forced consensus, debug rows, -outmat path
+  // states, seed-extension rows, verbose dumps, RAMCU_STATS); same CTA limit as fn[0]
+  extend_fn fnx;
 };
 
 // MAXT: wide lanes keep the whole 255-register budget (no spills); narrow lanes trade registers
@@ -41,19 +44,23 @@ constexpr int maxt2_for(int C)
 }
 #define RAMCU_CFG(B_, C_, G_)                                                                              \
   {B_, C_, G_, {maxt_for(C_), maxt2_for(C_)},                                                              \
-   {extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1>, extend_kernel<C_, G_, 2 * B_ + 1, maxt2_for(C_), 2>}}
+   {extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1, false>, extend_kernel<C_, G_, 2 * B_ + 1, maxt2_for(C_), 2, false>}, \
+   extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1, true>}
 // wide lanes: one pass per CTA only
 #define RAMCU_CFG1(B_, C_, G_) \
-  {B_, C_, G_, {maxt_for(C_), 0}, {extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1>, nullptr}}
+  {B_, C_, G_, {maxt_for(C_), 0}, {extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1, false>, nullptr}, \
+   extend_kernel<C_, G_, 2 * B_ + 1, maxt_for(C_), 1, true>}
 // same tiling with an explicit (larger) CTA limit: fewer registers per thread, more resident
 // instances -- the capacity fallback for very large families with wide bands
 #define RAMCU_CFG_T(B_, C_, G_, T_) \
-  {B_, C_, G_, {T_, 0}, {extend_kernel<C_, G_, 2 * B_ + 1, T_, 1>, nullptr}}
+  {B_, C_, G_, {T_, 0}, {extend_kernel<C_, G_, 2 * B_ + 1, T_, 1, false>, nullptr}, extend_kernel<C_, G_, 2 * B_ + 1, T_, 1, true>}
 #define RAMCU_GEN(C_, G_)                                                                \
   {-1, C_, G_, {maxt_for(C_), maxt2_for(C_)},                                            \
-   {extend_kernel<C_, G_, 0, maxt_for(C_), 1>, extend_kernel<C_, G_, 0, maxt2_for(C_), 2>}}
+   {extend_kernel<C_, G_, 0, maxt_for(C_), 1, false>, extend_kernel<C_, G_, 0, maxt2_for(C_), 2, false>}, \
+   extend_kernel<C_, G_, 0, maxt_for(C_), 1, true>}
 #define RAMCU_GEN1(C_, G_) \
-  {-1, C_, G_, {maxt_for(C_), 0}, {extend_kernel<C_, G_, 0, maxt_for(C_), 1>, nullptr}}
+  {-1, C_, G_, {maxt_for(C_), 0}, {extend_kernel<C_, G_, 0, maxt_for(C_), 1, false>, nullptr}, \
+   extend_kernel<C_, G_, 0, maxt_for(C_), 1, true>}
 
 struct CfgList
 {

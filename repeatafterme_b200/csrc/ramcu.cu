@@ -135,8 +135,12 @@ struct ramcu_job
   int *d_seed_rows = nullptr;   // seed extension: [L][n_ext][2]
   long long *d_dbg_wait = nullptr;   // RAMCU_STATS=1 diagnostics
   const KernelCfg *ran_cfg = nullptr;
+  int ran_passes = 1;         // passes per thread of the launch that ran the job
   int stats_ctas = 0;
   bool ran = false, in_batch = false;
+  // the job asks for a diagnostic / per-row output: it runs the instantiation that carries that code (cfg->fnx)
+  bool extras = false;
+  double plan_cost = 0;       // the cost model's figure for cfg (a column; of both passes when planned as a duo)
   unsigned long long timed_gen = 0;
 };
 
@@ -497,30 +501,36 @@ extern "C" int ramcu_library_free(ramcu_ctx *c, ramcu_library *lib)
 // ------------------------------------------------------------------------------------------
 // jobs
 // ------------------------------------------------------------------------------------------
-// np: 0 = one pass per CTA, 1 = both passes of a family in the same threads
+// np (kernel variant): 0 = one pass per CTA, 1 = both passes of a family in the same threads, 2 = one pass per
+// CTA with the diagnostic / per-row outputs compiled in (jobs with `extras`)
+static extend_fn fn_of(const KernelCfg *k, int np) { return np == 2 ? k->fnx : k->fn[np]; }
+static int maxt_of(const KernelCfg *k, int np) { return k->maxt[np == 2 ? 0 : np]; }
 static int ctas_per_sm(const KernelCfg *k, int np, int threads)
 {
   int nb = 0;
-  if (!k->fn[np] ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *) k->fn[np], threads, 0) != cudaSuccess)
+  if (!fn_of(k, np) ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *) fn_of(k, np), threads, 0) != cudaSuccess)
     return 0;
   return nb;
 }
 
-static int batch_threads(const KernelCfg *k, int np) { return std::min(kBatchThreads, k->maxt[np]); }
+static int batch_threads(const KernelCfg *k, int np) { return std::min(kBatchThreads, maxt_of(k, np)); }
 
 // Layout of one launch unit (a pass, or the two passes of a family) launched on its own: a single
 // CTA when it fits (no grid exchange at all), else 4-warp CTAs on distinct SMs, else the same number
 // of equally loaded CTAs on every SM (the column time is set by the most loaded scheduler, and
 // every CTA of the family waits for it).
-static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext, Plan *p)
+// duo: the unit is one of two single passes (the right and the left pass of a family) that will share the
+// device, each with this layout (ramcu_batch_run): twice the CTAs must be resident.
+static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext, Plan *p, bool duo = false)
 {
   const int ipw = inst_per_warp(k->G);
   const long long warps = ((long long) n_ext + ipw - 1) / ipw;
   const int sm = c->sm_count;
-  if (!k->fn[np])
+  const int units = duo ? 2 : 1;
+  if (!fn_of(k, np))
     return false;
-  if (warps * 32 <= k->maxt[np])
+  if (warps * 32 <= maxt_of(k, np))
   {
     p->n_ctas = 1;
     p->threads = (int) warps * 32;
@@ -530,7 +540,9 @@ static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext,
   {
     p->n_ctas = (int) std::min<long long>((warps + 3) / 4, n_ext);
     p->threads = cta_threads(n_ext, p->n_ctas, k->G);
-    return p->threads <= k->maxt[np];
+    if (p->threads > maxt_of(k, np))
+      return false;
+    return !duo || (long long) units * p->n_ctas <= (long long) ctas_per_sm(k, np, p->threads) * sm;
   }
   for (int per_sm = 1; per_sm <= 16; ++per_sm)
   {
@@ -538,9 +550,9 @@ static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext,
     if (n > n_ext)
       break;
     const int t = cta_threads(n_ext, (int) n, k->G);
-    if (t > k->maxt[np])
+    if (t > maxt_of(k, np))
       continue;
-    if (ctas_per_sm(k, np, t) < per_sm)
+    if (ctas_per_sm(k, np, t) < units * per_sm)
       continue;
     p->n_ctas = (int) n;
     p->threads = t;
@@ -552,7 +564,7 @@ static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext,
 // Layout when the unit shares a launch with others: fixed CTA size.
 static bool plan_batch(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext, int *n_ctas)
 {
-  if (!k->fn[np])
+  if (!fn_of(k, np))
     return false;
   const int threads = batch_threads(k, np);
   const int per_cta = (threads / 32) * inst_per_warp(k->G);
@@ -565,39 +577,50 @@ static bool plan_batch(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext
 
 // Rough cycles per column of a unit running alone (tuned on B200): a warp executes
 // about C*18 + 320 instructions per row and pass (C*15 + 250 when one lane holds the whole band);
-// one warp alone issues one every ~3 cycles (dependent max-plus chains), a loaded scheduler one
-// every ~1.8 cycles; the busiest of the four schedulers of the busiest SM sets the pace.
-static double solo_cost(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext, const Plan &p)
+// one warp alone issues one every ~3.4 cycles (dependent max-plus chains), a loaded scheduler one
+// every ~2.2 cycles; the busiest of the four schedulers of the busiest SM sets the pace. (Fitted to
+// tools/duo_sweep.py on B200: bandwidth 20-100, 50-10 000 instances; the choice is within a few per cent
+// of the best forced tiling except where neither two single-pass layouts nor a two-pass tiling fit.)
+// duo: cost of a column of BOTH passes when two single-pass units with this layout share the device.
+static double solo_cost(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext, const Plan &p, bool duo = false)
 {
-  const double passes = np ? 2.0 : 1.0;
-  // a tiling squeezed below ~2.4 registers per cell and pass keeps part of its rows in local memory
-  const double need = passes * (2.3 * k->C + 30.0) + 40.0;
-  const double squeeze = (65536.0 / k->maxt[np]) < need ? 1.5 : 1.0;
+  const double passes = np == 1 ? 2.0 : 1.0;
+  // a tiling whose row state does not fit its register budget keeps part of it in local memory (ptxas spills:
+  // the stack frame says how much)
+  double squeeze = 1.0;
+  {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, (const void *) fn_of(k, np)) == cudaSuccess)
+      squeeze = fa.localSizeBytes > 1024 ? 1.5 : fa.localSizeBytes > 256 ? 1.1 : 1.0;
+    else
+      (void) cudaGetLastError();
+  }
   const double instr = passes * ((k->G == 1 ? k->C * 15.0 + 250.0 : k->C * 18.0 + 320.0)) * squeeze;
   const int warps_per_cta = p.threads / 32;
-  const int ctas_on_sm = (p.n_ctas + c->sm_count - 1) / c->sm_count;
+  const int ctas_on_sm = ((duo ? 2 : 1) * p.n_ctas + c->sm_count - 1) / c->sm_count;
   const double per_sched = std::ceil(warps_per_cta * ctas_on_sm / 4.0);
   // one pass per CTA waits for every column's exchange; two passes hide each other's
-  const double sync = p.n_ctas > 1 ? (np ? 600.0 : 2400.0) : 0.0;
+  const double sync = p.n_ctas > 1 ? ((np == 1 || duo) ? 600.0 : 2400.0) : 0.0;
   (void) n_ext;
-  return std::max(instr * 3.0, per_sched * instr * 1.8) + sync;
+  return std::max(instr * 3.4, per_sched * instr * 2.2) + sync;
 }
 
 static const KernelCfg *pick_cfg(const ramcu_ctx *c, int np, int B, int n_ext, int force_G,
-                                 int concurrent_instances, int force_maxt, Plan *solo, int *batch_ctas)
+                                 int concurrent_instances, int force_maxt, Plan *solo, int *batch_ctas,
+                                 bool duo = false, double *cost_out = nullptr)
 {
   const int W = 2 * B + 1;
   std::vector<const KernelCfg *> cand;
   for (const KernelCfg *k : g_cfgs)
-    if (k->B == B && k->fn[np])
+    if (k->B == B && fn_of(k, np))
       cand.push_back(k);
   if (cand.empty())
     for (const KernelCfg *k : g_cfgs)
-      if (k->B < 0 && k->fn[np] && k->C * k->G >= W && (k->G - 1) * k->C < W)
+      if (k->B < 0 && fn_of(k, np) && k->C * k->G >= W && (k->G - 1) * k->C < W)
         cand.push_back(k);
   if (cand.empty())
     for (const KernelCfg *k : g_cfgs)  // narrow bands: trailing lanes may be entirely padding
-      if (k->B < 0 && k->fn[np] && k->C * k->G >= W)
+      if (k->B < 0 && fn_of(k, np) && k->C * k->G >= W)
       {
         cand.push_back(k);
         break;
@@ -609,22 +632,24 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int np, int B, int n_ext, i
   const bool crowded = concurrent_instances >= c->sm_count * 128;
   bool have_maxt = false;   // cta_thread_limit is a preference: ignored when no tiling of this band has it
   for (const KernelCfg *k : cand)
-    have_maxt = have_maxt || (k->maxt[np] == force_maxt && (force_G <= 0 || k->G == force_G));
+    have_maxt = have_maxt || (maxt_of(k, np) == force_maxt && (force_G <= 0 || k->G == force_G));
   for (const KernelCfg *k : cand)
   {
     if (force_G > 0 && k->G != force_G)
       continue;
-    if (force_maxt > 0 && k->maxt[np] != force_maxt && have_maxt)
+    if (force_maxt > 0 && maxt_of(k, np) != force_maxt && have_maxt)
       continue;
     Plan p;
     int nb = 0;
-    if (!plan_solo(c, k, np, n_ext, &p))
+    // (a tiling that fits alone but not twice still serves: the passes then run one after the other)
+    const bool duo_fits = duo && plan_solo(c, k, np, n_ext, &p, true);
+    if (!duo_fits && !plan_solo(c, k, np, n_ext, &p))
       continue;
     if (!plan_batch(c, k, np, n_ext, &nb))
       nb = 0;   // too large to share a launch: ramcu_batch_run launches it on its own
     // a crowded device is throughput bound: fewest lanes per instance = fewest instructions
-    const double cost = crowded ? (double) k->G + (k->maxt[np] > (np ? maxt2_for(k->C) : maxt_for(k->C)) ? 0.5 : 0.0)
-                                : solo_cost(c, k, np, n_ext, p);
+    const double cost = crowded ? (double) k->G + (maxt_of(k, np) > (np == 1 ? maxt2_for(k->C) : maxt_for(k->C)) ? 0.5 : 0.0)
+                                : solo_cost(c, k, np, n_ext, p, duo_fits) * ((duo && !duo_fits) ? 2.0 : 1.0);
     if (!best || cost < best_cost)
     {
       best = k;
@@ -633,6 +658,8 @@ static const KernelCfg *pick_cfg(const ramcu_ctx *c, int np, int B, int n_ext, i
       *batch_ctas = nb;
     }
   }
+  if (cost_out)
+    *cost_out = best_cost;
   return best;
 }
 
@@ -714,7 +741,7 @@ static void destroy_job(ramcu_ctx *c, ramcu_job *j)
 static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
                            const ramcu_core_t *cores, const ramcu_scoring_t *sc,
                            const ramcu_params_t *pr, int dbg_rows, const uint8_t *forced,
-                           ramcu_job **out, const int32_t *n_row = nullptr)
+                           ramcu_job **out, const int32_t *n_row = nullptr, bool duo = false)
 {
   if (!c || !lib || !sc || !pr || !out || (n_cores > 0 && !cores))
     return fail(RAMCU_ERR_ARG, "ramcu_job_create: NULL argument");
@@ -758,8 +785,10 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
 
   if (j->n_ext > 0 && pr->L > 0)
   {
-    j->cfg = pick_cfg(c, 0, B, j->n_ext, pr->lanes_per_instance, pr->concurrent_instances, pr->cta_thread_limit,
-                      &j->solo, &j->batch_ctas);
+    // which outputs are asked for is known from the arguments: lay the job out for the kernel variant it will run
+    j->extras = dbg_rows != 0 || forced != nullptr || getenv("RAMCU_STATS") != nullptr;
+    j->cfg = pick_cfg(c, j->extras ? 2 : 0, B, j->n_ext, pr->lanes_per_instance, pr->concurrent_instances, pr->cta_thread_limit,
+                      &j->solo, &j->batch_ctas, duo, &j->plan_cost);
     if (!j->cfg)
     {
       destroy_job(c, j);
@@ -906,9 +935,11 @@ static int launch_single(ramcu_ctx *c, ramcu_job *j)
     j->fam_dirty = false;
   }
   j->ran_cfg = j->cfg;
+  j->ran_passes = 1;
   j->stats_ctas = j->solo.n_ctas;
-  int rc = launch_unit(c, j->cfg->fn[0], j->solo.n_ctas, j->solo.threads, j->d_fam, j->d_cta_fam, j->solo.n_ctas > 1,
-                       ctas_per_sm(j->cfg, 0, j->solo.threads));
+  const int v = j->extras ? 2 : 0;
+  int rc = launch_unit(c, fn_of(j->cfg, v), j->solo.n_ctas, j->solo.threads, j->d_fam, j->d_cta_fam, j->solo.n_ctas > 1,
+                       ctas_per_sm(j->cfg, v, j->solo.threads));
   if (rc)
     return rc;
   return enqueue_fetch(c, j);
@@ -984,6 +1015,7 @@ extern "C" int ramcu_job_fetch(ramcu_ctx *c, ramcu_job *j, uint8_t *master_out, 
   res->max_score = r4[3];
   res->hit_limit = (r4[2] >= 0 && r4[2] == j->pr.L - 1) ? 1 : 0;
   res->lanes_per_instance = j->ran_cfg ? j->ran_cfg->G : j->cfg->G;
+  res->passes_per_thread = j->ran_passes;
   if (j->timed_gen != 0 && j->timed_gen == c->launch_gen)
   {
     float ms = 0.f;
@@ -1101,6 +1133,7 @@ struct Unit
   const KernelCfg *cfg;
   int np, n_ctas;
   long long work;
+  int threads = 0;    // > 0: CTA size of this unit's launch (its own layout) instead of batch_threads()
 };
 
 extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
@@ -1148,7 +1181,7 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
       continue;
     }
     if (j->batch_ctas > 0)
-      units.push_back(Unit{j, nullptr, j->cfg, 0, j->batch_ctas, (long long) j->n_ext * j->pr.L});
+      units.push_back(Unit{j, nullptr, j->cfg, j->extras ? 2 : 0, j->batch_ctas, (long long) j->n_ext * j->pr.L});
     else
       alone.push_back(j);
     j->in_batch = false;
@@ -1156,13 +1189,38 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
   if (units.size() == 1 && alone.empty())
   {
     // nothing shares the device with this unit: lay it out as a launch of its own
-    if (units[0].np == 0)
+    if (units[0].np != 1)
     {
       alone.push_back(units[0].a);
       units.clear();
     }
     else
       units[0].n_ctas = -units[0].a->pair_solo.n_ctas;
+  }
+  if (units.size() + alone.size() == 2 && (units.empty() || units[0].np != 1) && (units.size() < 2 || units[1].np != 1))
+  {
+    // two single passes with the device to themselves (the right and the left pass of a family whose tiling
+    // holds one row state per thread): each keeps the layout it would have alone -- equally loaded CTAs on every
+    // SM -- and the two share one launch, so that one pass computes while the other's column sums travel
+    ramcu_job *d[2];
+    int n = 0;
+    for (const Unit &u : units)
+      d[n++] = u.a;
+    for (ramcu_job *j : alone)
+      d[n++] = j;
+    if (d[0]->cfg == d[1]->cfg && d[0]->extras == d[1]->extras && d[0]->solo.threads == d[1]->solo.threads &&
+        d[0]->solo.n_ctas + d[1]->solo.n_ctas <=
+            ctas_per_sm(d[0]->cfg, d[0]->extras ? 2 : 0, d[0]->solo.threads) * c->sm_count)
+    {
+      units.clear();
+      alone.clear();
+      for (ramcu_job *j : d)
+      {
+        Unit u{j, nullptr, j->cfg, j->extras ? 2 : 0, j->solo.n_ctas, (long long) j->n_ext * j->pr.L};
+        u.threads = j->solo.threads;
+        units.push_back(u);
+      }
+    }
   }
   std::stable_sort(units.begin(), units.end(), [](const Unit &x, const Unit &y) {
     if ((x.n_ctas < 0) != (y.n_ctas < 0))
@@ -1190,7 +1248,7 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
     std::vector<FamDev> fams;
     std::vector<int> cta_fam;
     bool multi = false;
-    int threads = solo ? units[p].a->pair_solo.threads : batch_threads(cfg, np);
+    int threads = solo ? units[p].a->pair_solo.threads : units[p].threads > 0 ? units[p].threads : batch_threads(cfg, np);
     while (q < units.size() && units[q].cfg == cfg && units[q].np == np && (units[q].n_ctas < 0) == solo)
     {
       const Unit &u = units[q];
@@ -1203,6 +1261,7 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
         cta_fam.push_back((int) fams.size());
       fams.push_back(f);
       u.a->ran_cfg = cfg;
+      u.a->ran_passes = u.b ? 2 : 1;
       u.a->stats_ctas = std::min(n_ctas, u.a->max_ctas);
       if (u.b)
       {
@@ -1212,6 +1271,7 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
         g.mate = -1;
         fams.push_back(g);
         u.b->ran_cfg = cfg;
+        u.b->ran_passes = 2;
         u.b->stats_ctas = 0;
       }
       if (n_ctas > 1)
@@ -1233,7 +1293,7 @@ extern "C" int ramcu_batch_run(ramcu_ctx *c, int n_jobs, ramcu_job **jobs)
     // pageable sources: the copies are staged before the calls return, so the vectors may go away
     CK(cudaMemcpyAsync(d_fams, fams.data(), fams.size() * sizeof(FamDev), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_map, cta_fam.data(), cta_fam.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    int rc = launch_unit(c, cfg->fn[np], (int) cta_fam.size(), threads, d_fams, d_map, multi, ctas_per_sm(cfg, np, threads));
+    int rc = launch_unit(c, fn_of(cfg, np), (int) cta_fam.size(), threads, d_fams, d_map, multi, ctas_per_sm(cfg, np, threads));
     if (rc)
       return rc;
     CK(cudaFreeAsync(d_fams, c->stream));
@@ -1272,9 +1332,10 @@ extern "C" int ramcu_job_create_pair(ramcu_ctx *c, ramcu_library *lib, int n_cor
   if (!c || !pr || !right || !left || (n_cores > 0 && !cores))
     return fail(RAMCU_ERR_ARG, "ramcu_job_create_pair: NULL argument");
   *right = *left = nullptr;
-  int rc = job_create_impl(c, lib, 1, n_cores, cores, sc, pr, 0, nullptr, right);
+  // each pass is laid out as one of two single-pass units that share the device (ramcu_batch_run) ...
+  int rc = job_create_impl(c, lib, 1, n_cores, cores, sc, pr, 0, nullptr, right, nullptr, true);
   if (!rc)
-    rc = job_create_impl(c, lib, 0, n_cores, cores, sc, pr, 0, nullptr, left);
+    rc = job_create_impl(c, lib, 0, n_cores, cores, sc, pr, 0, nullptr, left, nullptr, true);
   if (rc)
   {
     ramcu_job_free(c, *right);
@@ -1284,11 +1345,17 @@ extern "C" int ramcu_job_create_pair(ramcu_ctx *c, ramcu_library *lib, int n_cor
   ramcu_job *a = *right, *b = *left;
   if (a->n_ctas > 0 && b->n_ctas > 0 && !getenv("RAMCU_NO_PAIR"))   // RAMCU_NO_PAIR: tuning aid
   {
+    // ... unless both passes in the same threads are expected to be faster: that pays where the column exchange
+    // dominates and the family is too large for two single-pass layouts side by side
     Plan solo;
     int nb = 0;
+    double pair_cost = 0;
     const KernelCfg *k = pick_cfg(c, 1, pr->bandwidth, std::max(a->n_ext, b->n_ext), pr->lanes_per_instance,
-                                  pr->concurrent_instances, pr->cta_thread_limit, &solo, &nb);
-    if (k && solo.n_ctas <= std::min(a->max_ctas, b->max_ctas))
+                                  pr->concurrent_instances, pr->cta_thread_limit, &solo, &nb, false, &pair_cost);
+    const bool crowded = pr->concurrent_instances >= c->sm_count * 128;
+    const bool duo_better = !crowded && !getenv("RAMCU_PAIR_ALWAYS") && a->cfg == b->cfg &&
+                            a->solo.threads == b->solo.threads && std::max(a->plan_cost, b->plan_cost) <= pair_cost;
+    if (k && !duo_better && solo.n_ctas <= std::min(a->max_ctas, b->max_ctas))
     {
       if (nb > std::min(a->max_ctas, b->max_ctas))
         nb = 0;

@@ -92,12 +92,14 @@ static int launch(LaunchArgs proto, int grid, int block)
   return 0;
 }
 
-struct Cfg { int C, G, WS; extend_fn fn, fn2; };
-#define ECFG(C_, G_, WS_) {C_, G_, WS_, extend_kernel<C_, G_, WS_, 1024, 1>, extend_kernel<C_, G_, WS_, 1024, 2>}
+struct Cfg { int C, G, WS; extend_fn fn, fn2, fnx; };   // lean single pass, two passes, single pass with extras
+#define ECFG(C_, G_, WS_) \
+  {C_, G_, WS_, extend_kernel<C_, G_, WS_, 1024, 1, false>, extend_kernel<C_, G_, WS_, 1024, 2, false>, \
+   extend_kernel<C_, G_, WS_, 1024, 1, true>}
 static const Cfg kCfgs[] = {
   ECFG(11, 1, 11), ECFG(6, 2, 11), ECFG(3, 4, 11), ECFG(4, 3, 11),      // B = 5, static band
   ECFG(29, 1, 29), ECFG(15, 2, 29), ECFG(8, 4, 29), ECFG(4, 8, 29),     // B = 14
-  ECFG(21, 4, 81), ECFG(11, 8, 81), ECFG(41, 2, 81), ECFG(27, 3, 81), ECFG(17, 5, 81),   // B = 40
+  ECFG(21, 4, 81), ECFG(11, 8, 81), ECFG(41, 2, 81), ECFG(27, 3, 81), ECFG(17, 5, 81), ECFG(81, 1, 81),   // B = 40
   ECFG(10, 3, 29), ECFG(5, 6, 29),
   ECFG(4, 4, 0), ECFG(8, 4, 0), ECFG(16, 4, 0), ECFG(32, 4, 0), ECFG(16, 16, 0), ECFG(16, 32, 0), ECFG(8, 5, 0), ECFG(16, 7, 0),
 };
@@ -196,7 +198,8 @@ static int emul_extend_impl(int C, int G, int WS, int threads, const uint8_t *se
   }
   int ticket = 0;
   LaunchArgs a = {};
-  a.fn = cfg->fn;
+  // as in ramcu.cu: the lean instantiation unless a diagnostic / per-row output is asked for
+  a.fn = (f.forced || f.dbg_rows || f.dbg_best || f.dbg_path || f.seed_rows) ? cfg->fnx : cfg->fn;
   a.fams = &f;
   a.cta_fam = cta_fam.data();
   a.ticket = &ticket;
@@ -446,7 +449,7 @@ extern "C" int emul_seed_rows(int C, int G, int WS, const uint8_t *seq, uint64_t
   f.seed_rows = srows.data();
   int ticket = 0;
   LaunchArgs a = {};
-  a.fn = cfg->fn;
+  a.fn = cfg->fnx;
   a.fams = &f;
   a.cta_fam = cta_fam.data();
   a.ticket = &ticket;

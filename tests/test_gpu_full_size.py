@@ -33,9 +33,11 @@ def _params(case, **over):
     return matrix, make_params(**p)
 
 
-def test_config4_full_equals_reference(ramcu):
-    """BASELINE configs[3] at full size (10 000 instances, 5 kb flanks, 2 x 5100 columns): the pair
-    launch bench.py times, the two-call form, and a second tiling == the reference's outputs"""
+def test_config4_full_equals_reference(ramcu, monkeypatch):
+    """BASELINE configs[3] at full size (10 000 instances, 5 kb flanks, 2 x 5100 columns): the launch of
+    both passes that bench.py times (the form the planner picks: two single-pass units sharing the launch),
+    both passes in the same threads (RAMCU_PAIR_ALWAYS), the two-call form, and a second tiling == the
+    reference's outputs"""
     case = gio.load_full("config4")["seed4"]
     fam = full_case_family("config4", "seed4")
     gio.check_full_inputs(fam, case)
@@ -46,6 +48,11 @@ def test_config4_full_equals_reference(ramcu):
         pair = ramcu.extend_pair(lib, fam.cores, sc, p)
         for d, o in zip((1, 0), pair):
             _check(case["want"][d], _got(*o), f"pair launch dir={d}")
+        monkeypatch.setenv("RAMCU_PAIR_ALWAYS", "1")
+        pair = ramcu.extend_pair(lib, fam.cores, sc, p)
+        monkeypatch.delenv("RAMCU_PAIR_ALWAYS")
+        for d, o in zip((1, 0), pair):
+            _check(case["want"][d], _got(*o), f"both passes in the same threads dir={d}")
         for G in (0, 5):
             _, pg = _params(case, lanes_per_instance=G)
             for d in (1, 0):

@@ -179,20 +179,27 @@ def test_batch_with_and_without_between_passes_hook(ramcu):
     (114, 400, 200, 100, "25p43g", dict(pad=3)),
     (115, 500, 200, 33, "18p43g", dict()),                                   # runtime-width tiling
 ])
-def test_pair_launch_vs_oracle(ramcu, oracle, seed, n, flank, B, matrix, kw):
+def test_pair_launch_vs_oracle(ramcu, oracle, seed, n, flank, B, matrix, kw, monkeypatch):
     """ramcu_extend_pair (right and left pass of one family sharing one launch) == oracle ==
-    two separate ramcu_extend calls, including families with one-side-extendable cores"""
+    two separate ramcu_extend calls, including families with one-side-extendable cores; in the form
+    the planner picks, as two single-pass units sharing the launch (RAMCU_NO_PAIR) and with both
+    passes in the same threads (RAMCU_PAIR_ALWAYS)"""
     fam = synth.make_family(seed, n, flank, 0.15, **kw)
     osc = oracle.scoring(matrix)
     lib = ramcu.upload_library(fam.sequence)
     try:
         p = make_params(bandwidth=B, minimprovement=27, L=20000)
-        pair = [_got(*o) for o in ramcu.extend_pair(lib, fam.cores, osc.to_product(), p)]
-        for d, got in zip((1, 0), pair):
-            want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
-            support.compare_extend(want, got, f"pair seed={seed} dir={d}")
-            alone = _got(*ramcu.extend(lib, d, fam.cores, osc.to_product(), p))
-            support.compare_extend(alone, got, f"pair vs alone seed={seed} dir={d}")
+        want = [oracle.extend(d, fam.cores, fam.sequence, osc, p) for d in (1, 0)]
+        alone = [_got(*ramcu.extend(lib, d, fam.cores, osc.to_product(), p)) for d in (1, 0)]
+        for env in (None, "RAMCU_NO_PAIR", "RAMCU_PAIR_ALWAYS"):
+            monkeypatch.delenv("RAMCU_NO_PAIR", raising=False)
+            monkeypatch.delenv("RAMCU_PAIR_ALWAYS", raising=False)
+            if env:
+                monkeypatch.setenv(env, "1")
+            pair = [_got(*o) for o in ramcu.extend_pair(lib, fam.cores, osc.to_product(), p)]
+            for d, got, w, a in zip((1, 0), pair, want, alone):
+                support.compare_extend(w, got, f"pair ({env}) seed={seed} dir={d}")
+                support.compare_extend(a, got, f"pair ({env}) vs alone seed={seed} dir={d}")
     finally:
         ramcu.free_library(lib)
 
@@ -254,15 +261,14 @@ def test_full_size_properties(ramcu):
     lib = ramcu.upload_library(fam.sequence)
     outs = {}
     try:
-        for G in (2, 3, 4):
+        for G in (1, 2, 3, 4):
             p = make_params(bandwidth=40, minimprovement=30, L=20000, lanes_per_instance=G)
             outs[G] = [_got(*ramcu.extend(lib, d, fam.cores, sc, p)) for d in (1, 0)]
-        outs[1] = outs[2]
-        for G in (3, 4):
+        for G in (2, 3, 4):
             for a, b in zip(outs[1], outs[G]):
-                support.compare_extend(a, b, f"G=2 vs G={G}")
+                support.compare_extend(a, b, f"G=1 vs G={G}")
         assert outs[1][0]["extended_bp"] > 1000 and outs[1][1]["extended_bp"] > 1000
-        # both passes in one launch (20 000 instance-bands: only the half-register tiling fits)
+        # both passes in one launch, in the form the planner picks
         pair = [_got(*o) for o in ramcu.extend_pair(lib, fam.cores, sc, make_params(bandwidth=40, minimprovement=30, L=20000))]
         for a, b in zip(outs[1], pair):
             support.compare_extend(a, b, "separate passes vs pair launch")
