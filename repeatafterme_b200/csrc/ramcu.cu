@@ -536,6 +536,18 @@ static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext,
     p->threads = (int) warps * 32;
     return true;
   }
+  // RAMCU_DUO_SPREAD (tuning aid): from how many warps per pass, in per cent of the SM count (0 = never)
+  static const int spread_from = getenv("RAMCU_DUO_SPREAD") ? atoi(getenv("RAMCU_DUO_SPREAD")) : 100;
+  if (duo && spread_from > 0 && warps >= (long long) spread_from * sm / 100 && warps <= (long long) sm * 4)
+  {
+    // both passes on every SM: a CTA of each pass per SM, so that each SM has the other pass's rows to compute
+    // while one pass's column sums travel (config 4: 18.5 -> 17.3 ms against 4-warp CTAs on distinct SMs, where
+    // most SMs hold one pass only)
+    p->n_ctas = sm;
+    p->threads = cta_threads(n_ext, p->n_ctas, k->G);
+    if (p->threads <= maxt_of(k, np) && ctas_per_sm(k, np, p->threads) >= 2)
+      return true;
+  }
   if (warps <= (long long) sm * 4)
   {
     p->n_ctas = (int) std::min<long long>((warps + 3) / 4, n_ext);
@@ -585,13 +597,15 @@ static bool plan_batch(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext
 static double solo_cost(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext, const Plan &p, bool duo = false)
 {
   const double passes = np == 1 ? 2.0 : 1.0;
-  // a tiling whose row state does not fit its register budget keeps part of it in local memory (ptxas spills:
-  // the stack frame says how much)
-  double squeeze = 1.0;
+  // a tiling squeezed below ~2.3 registers per cell and pass keeps part of its rows in local memory; so does one
+  // whose stack frame (ptxas spills) is large: the 41-cell lanes at 168 registers
+  const double need = passes * (2.28 * k->C + 30.0) + 40.0;
+  double squeeze = (65536.0 / maxt_of(k, np)) < need ? 1.5 : 1.0;
+  if (squeeze == 1.0)
   {
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, (const void *) fn_of(k, np)) == cudaSuccess)
-      squeeze = fa.localSizeBytes > 1024 ? 1.5 : fa.localSizeBytes > 256 ? 1.1 : 1.0;
+      squeeze = (int) fa.localSizeBytes > 2 * fa.numRegs ? 1.3 : (int) fa.localSizeBytes > fa.numRegs ? 1.1 : 1.0;   // stack bytes per register
     else
       (void) cudaGetLastError();
   }
