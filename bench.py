@@ -182,6 +182,40 @@ def workload_config(n_gpus: int) -> dict:
 
 
 # ---------------------------------------------------------------------------------------------
+# the product CLI on the same family: what a RAMExtend user sees
+# ---------------------------------------------------------------------------------------------
+def cli_leg(fam, runs=2):
+    """bin/RAMExtend (the reference's unmodified main() linked with this repo's extend_alignment() and flank
+    loader) on the config-4 family written as .2bit + ranges files: wall seconds of the whole process (CUDA context
+    creation, .2bit loading, both passes, overlap avoidance, report, -cons / -outtsv / -outfa), with the breakdown
+    the boundary prints under RAMX_TIMING=1. The first run warms the page cache and is not reported."""
+    import tempfile
+    from repeatafterme_b200 import synth
+    exe = os.path.join(ROOT, "repeatafterme_b200", "bin", "RAMExtend")
+    if not os.path.exists(exe):
+        return {"unavailable": "bin/RAMExtend not built (needs the reference's host objects, oracle/_ref)"}
+    with tempfile.TemporaryDirectory() as tmp:
+        tb, rg = os.path.join(tmp, "f.2bit"), os.path.join(tmp, "f.tsv")
+        synth.write_family_files(fam, tb, rg)
+        cmd = [exe, "-twobit", tb, "-ranges", rg, "-outtsv", os.path.join(tmp, "o.tsv"), "-outfa", os.path.join(tmp, "o.fa"),
+               "-cons", os.path.join(tmp, "c.fa"), "-bandwidth", str(WORKLOAD["bandwidth"]), "-matrix", WORKLOAD["matrix"],
+               "-minimprovement", str(WORKLOAD["minimprovement"]), "-L", str(WORKLOAD["L"])]
+        walls, r = [], None
+        for _ in range(runs + 1):
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, RAMX_TIMING="1"))
+            walls.append(time.perf_counter() - t0)
+            if r.returncode != 0:
+                return {"unavailable": "bin/RAMExtend exited %d: %s" % (r.returncode, (r.stdout + r.stderr)[-300:])}
+        ext = [l.strip() for l in r.stdout.splitlines() if l.startswith("Extended")]
+        return {"wall_s": round(min(walls[1:]), 3), "runs": [round(w, 3) for w in walls[1:]],
+                "breakdown": [l[len("[ramx timing] "):] for l in r.stderr.splitlines() if l.startswith("[ramx timing]")],
+                "extended": ext, "outputs": "-cons -outtsv -outfa written",
+                "what": "wall clock of the whole bin/RAMExtend process on BASELINE config 4 as .2bit + ranges files "
+                        "(context creation + loader + both passes + overlap avoidance + report + three output files)"}
+
+
+# ---------------------------------------------------------------------------------------------
 # BASELINE configs[4]: synthetic genome-scale round
 # ---------------------------------------------------------------------------------------------
 def config5_round(args, rc, stream, world, rank, local, barrier, peak_gops):
@@ -473,6 +507,11 @@ def run_cuda(args):
     del dev_seq
 
     n_bases = int(fam.sequence.size)
+    cli = None
+    if rank == 0 and world == 1 and not args.no_cli and n == WORKLOAD["n"] and flank == WORKLOAD["flank"]:
+        torch.cuda.synchronize()
+        cli = cli_leg(fam)
+        log(f"[cli] {cli}")
     # the single-family leg is done: release it before the genome-scale round
     for j in jobs:
         rc.job_free(j)
@@ -591,6 +630,8 @@ def run_cuda(args):
                                    "on the device) instead of the reference loader's 1 byte per base"},
             "gpu_launches": (2 if args.sequential else 1) * args.steps,
             "clocks": clocks}
+    if cli:
+        line["cli"] = cli
     if fam_info:
         line["family_batch"] = fam_info
     print(json.dumps(line), file=json_out, flush=True)
@@ -613,6 +654,7 @@ def main():
     ap.add_argument("--families", type=int, default=-1,
                     help="genome-scale round (BASELINE configs[4]): -1 = all 2000 families, K > 0 = a seeded subset of K, "
                          "0 = skip")
+    ap.add_argument("--no-cli", action="store_true", help="skip the product CLI wall-clock leg (N=1 only)")
     ap.add_argument("--family-runs", type=int, default=2, help="timed runs of the genome-scale round per leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

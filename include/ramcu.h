@@ -27,6 +27,8 @@
  *                        util/extend-stk.pl:365-371) share one context and run concurrently
  *   ramcu_seed_extend_batch / ramcu_global_align
  *                        cons_seed_extend() / pair_seed_extend() / global_align()  bnw_extend.c:167-649
+ *   ramcu_extend_paths   the -outmat branch of extend_alignment()           ram_extend.c:1115-1132
+ *   ramcu_extend_verbose the VERBOSE >= 10 dumps of extend_alignment()       ram_extend.c:949-959, 992-1090, 1177-1214
  *   ramcu_debug_rows     compute_nw_row() as called by the reference's unit tests
  *                        (bnw_extend.c:1583,1600): forced consensus, band rows returned
  */
@@ -212,6 +214,22 @@ int ramcu_extend_paths(ramcu_ctx *ctx, ramcu_library *lib, int direction, int n_
                        const ramcu_params_t *params, uint8_t *master_out, int32_t *ext_len_out,
                        int32_t *score_add_out, ramcu_result_t *res, uint8_t *path_state_out,
                        int32_t *row_best_out, int32_t *row_best_idx_out);
+
+/* VERBOSE >= 10 dumps (ram_extend.c:992-1090, 1139-1141, 1177-1214): ramcu_extend() that also returns, for the
+ * first n_rows processed rows r, every core i extendable in `direction` and every candidate consensus base a,
+ *   cand_out[((r * n_cores + i) * 4 + a) * 4 + 0]   compute_nw_row()'s return value (curr_row_best_score, unclamped)
+ *                                            + 1   *max_score_sequence_idx (curr_row_best_col_idx)
+ *                                            + 2   gap value of band cell 0      (score[row%2][n][0][1])
+ *                                            + 3   gap value of band cell 2B     (score[row%2][n][2*BANDWIDTH][1])
+ *   sums_out[r * 4 + a]                             score_given_cons
+ *   cells_out (or NULL; VERBOSE >= 12)              [n_rows][n_cores][4][2B+1][2] = (sub, gap) of every band cell
+ * everything a caller needs to print the reference's per-row dumps without any DP on the host
+ * (csrc/ramx_boundary.c does). Entries of cores not extendable in `direction` are left untouched. */
+int ramcu_extend_verbose(ramcu_ctx *ctx, ramcu_library *lib, int direction, int n_cores,
+                         const ramcu_core_t *cores, const ramcu_scoring_t *scoring,
+                         const ramcu_params_t *params, uint8_t *master_out, int32_t *ext_len_out,
+                         int32_t *score_add_out, ramcu_result_t *res, int n_rows, int32_t *cand_out,
+                         int32_t *sums_out, int32_t *cells_out);
 
 /* Seed extension: the other callers of compute_nw_row() (bnw_extend.c:167-649), batched.
  * One ramcu_seed_t == one cons_seed_extend() call (bnw_extend.h:38-43): the query (host codes 0..3, any

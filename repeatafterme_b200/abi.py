@@ -37,6 +37,7 @@ ABI_SYMBOLS = (
     "ramcu_library_from_device", "ramcu_library_from_twobit", "ramcu_library_download", "ramcu_library_free", "ramcu_extend", "ramcu_job_create",
     "ramcu_job_run", "ramcu_job_fetch", "ramcu_job_free", "ramcu_batch_run", "ramcu_debug_rows",
     "ramcu_job_create_pair", "ramcu_extend_pair", "ramcu_extend_paths", "ramcu_seed_extend_batch", "ramcu_global_align",
+    "ramcu_extend_verbose",
 )
 
 
@@ -159,6 +160,8 @@ def load_ramcu(path: str = LIB_PATH) -> C.CDLL:
                                       vp, vp, vp, P(ExtendResult)]
     lib.ramcu_extend_paths.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult),
                                        vp, vp, vp]
+    lib.ramcu_extend_verbose.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult),
+                                         i32, vp, vp, vp]
     lib.ramcu_seed_extend_batch.argtypes = [vp, vp, i32, vp, P(Scoring), vp, i32, i32, vp]
     lib.ramcu_global_align.argtypes = [vp, vp, i32, vp, i32, C.c_int64, C.c_int64, P(Scoring), vp, i32, P(i32), P(i32), P(i32)]
     lib.ramcu_debug_rows.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), i32, vp, vp, vp, vp]
@@ -285,6 +288,28 @@ class RamCu:
                                                 best.ctypes.data, idx.ctypes.data))
         rp = res.rows_processed
         return res, master[:rp].copy(), ext_len, score_add, state[:rp], best[:rp], idx[:rp]
+
+    def extend_verbose(self, lib_h, direction: int, cores: np.ndarray, scoring: Scoring, params: Params,
+                       n_rows: int, cells: bool = False):
+        """ramcu_extend_verbose: extend() plus, for the first n_rows rows, what compute_nw_row() returned and left
+        behind for every candidate base (the data of the reference's VERBOSE >= 10 dumps): cand[r, core, a] =
+        (best, best column index, gap of band cell 0, gap of band cell 2B), sums[r, a], and with cells=True the
+        (sub, gap) pair of every band cell of every candidate's row."""
+        cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+        n, W, L = cores.size, 2 * params.bandwidth + 1, max(params.L, 1)
+        master = np.zeros(L, dtype=np.uint8)
+        ext_len = np.zeros(n, dtype=np.int32)
+        score_add = np.zeros(n, dtype=np.int32)
+        cand = np.zeros((max(n_rows, 1), n, 4, 4), dtype=np.int32)
+        sums = np.zeros((max(n_rows, 1), 4), dtype=np.int32)
+        cel = np.zeros((max(n_rows, 1), n, 4, W, 2), dtype=np.int32) if cells else None
+        res = ExtendResult()
+        self._check(self.lib.ramcu_extend_verbose(self.ctx, lib_h, direction, n, cores.ctypes.data, C.byref(scoring),
+                                                  C.byref(params), master.ctypes.data, ext_len.ctypes.data,
+                                                  score_add.ctypes.data, C.byref(res), n_rows, cand.ctypes.data,
+                                                  sums.ctypes.data, cel.ctypes.data if cells else None))
+        rp = min(res.rows_processed, n_rows)
+        return res, master[:res.rows_processed].copy(), ext_len, score_add, cand[:rp], sums[:rp], (cel[:rp] if cells else None)
 
     # -- split form -------------------------------------------------------------------------
     def job_create(self, lib_h, direction: int, cores: np.ndarray, scoring: Scoring, params: Params):

@@ -81,11 +81,17 @@ struct FamDev
   int *dbg_idx;           // -outmat: [rows][n_ext] band index of the row's first best cell
   int *seed_rows;         // seed extension: [rows][n_ext][2] = compute_nw_row()'s return value for the given
                           // consensus base and *max_score_sequence_idx (bnw_extend.c:1020-1024)
+  int *dbg_cand;          // verbose dumps (VERBOSE >= 10, ram_extend.c:992-1075): [dbg_nrows][n_ext][4][3] per candidate
+                          // base: *max_score_sequence_idx of its row, the gap value of band cell 0 and of band
+                          // cell 2B (the reference's **OUT_OF_SEQ** tests, ram_extend.c:1037-1039, 1139-1141)
+  int *dbg_cells;         // VERBOSE >= 12 (ram_extend.c:1013-1024): [dbg_nrows][n_ext][4][W][2] (sub, gap) of every
+                          // candidate's row (or NULL)
   long long *dbg_wait;    // diagnostics: per CTA [0] cycles spent in the grid exchange [1] total cycles
   int n_ext, n_ctas, cta0, B;
   int W, go, ge, cap;
   int minimp, L, stop;
   int mate;               // index of the family's other pass in the same launch (two-pass CTAs), or -1
+  int dbg_nrows;          // rows the dbg_cand / dbg_cells arrays hold
   int m[8][4];            // m[code][cand]; code 4 = N, 5 = out of bounds (value unused)
   int mN[8];              // mN[code]: score of an N consensus base (forced consensus 4, seed extension)
 };
@@ -321,6 +327,48 @@ __device__ __forceinline__ int exact_pass(int (&Pp)[C], int (&Dd)[C], const uint
   return hprev;
 }
 
+// Row of candidate base a WITHOUT committing it, for the verbose dumps: the same cell loop as exact_pass
+// with the true hin; reports the lane's first cell equal to bestv, the gap value of band cell 0 / W-1 when
+// the lane owns it, and (cells != NULL) the (sub, gap) pair of every real cell.
+template <int C>
+__device__ __forceinline__ void probe_pass(const int (&Pp)[C], const int (&Dd)[C], const uint32_t *win,
+                                           const char *lutb, const int a, const int go, const int ge,
+                                           const int hin, const int gl, const int W, const int B, const int r,
+                                           const int tmin, const int tmax, const int bestv, int &idx,
+                                           int &g_first, int &g_last, int *cells)
+{
+  const int goe = go + ge;
+  const int edge = go + (r + 1) * ge;
+  const int tbase = r - B + gl * C;
+  int hprev = hin;
+  idx = kBig;
+#pragma unroll
+  for (int k = 0; k < C; ++k)
+  {
+    const int K = gl * C + k;
+    const bool real = K < W;
+    const int t = tbase + k;
+    const bool inb = real && (t >= tmin) && (t <= tmax);
+    const int E = (K < B && r < B) ? edge : kOob;
+    const int Dk = (K >= W - 1) ? kNeg : Dd[k];
+    const int m = *reinterpret_cast<const int *>(lutb + win_byte(win[k >> 2], k & 3) + 4 * a);
+    const int S = inb ? Pp[k] + m : E;
+    const int Gv = inb ? imax(Dk, hprev) : E;
+    const int pn = imax(S, Gv);
+    idx = min(idx, (real && pn == bestv) ? k : kBig);
+    if (K == 0)
+      g_first = Gv;
+    if (K == W - 1)
+      g_last = Gv;
+    if (cells != nullptr && real)
+    {
+      cells[2 * K] = S;
+      cells[2 * K + 1] = Gv;
+    }
+    hprev = imax(S + goe, Gv + ge);
+  }
+}
+
 // True H of the cell left of each lane from the lanes' local aggregates: an (aggregate, transfer)
 // max-plus scan over the G lanes of an instance. `agg` = H of the lane's last cell computed with no
 // carry-in; `open` = every cell of the lane is an in-bounds band cell (an out-of-bounds cell restarts
@@ -508,7 +556,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
 
   const FamDev *Fp[NP];
   PassRegs<C> ps[NP];
-  bool dbg_on[NP], use_fast[NP], has_forced[NP], has_dbg_best[NP], has_dbg_path[NP], has_seed_rows[NP];
+  bool dbg_on[NP], use_fast[NP], has_forced[NP], has_dbg_best[NP], has_dbg_path[NP], has_seed_rows[NP], has_dbg_cand[NP];
 
   // ---- set-up of every pass: instance, boundary row, first base window ------------------------
 #pragma unroll
@@ -533,11 +581,12 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     S.tmax = I.tmax;
     // forced consensus, debug rows, -outmat states and per-row seed values exist for single passes only
     // (ramcu_job_create_pair never asks for them): the two-pass kernel carries none of that code
-    dbg_on[p] = kExtras && ((F->dbg_rows != nullptr) || (F->dbg_path != nullptr));
+    dbg_on[p] = kExtras && ((F->dbg_rows != nullptr) || (F->dbg_path != nullptr) || (F->dbg_cand != nullptr));
     has_forced[p] = kExtras && F->forced != nullptr;
     has_dbg_best[p] = kExtras && F->dbg_best != nullptr;
     has_dbg_path[p] = kExtras && F->dbg_path != nullptr;
     has_seed_rows[p] = kExtras && F->seed_rows != nullptr;
+    has_dbg_cand[p] = kExtras && F->dbg_cand != nullptr;
     use_fast[p] = (WS != 0) && gaps_ok && !dbg_on[p];
 #pragma unroll
     for (int i = 0; i < CW; ++i)
@@ -664,6 +713,38 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
 #pragma unroll
       for (int a = 0; a < 4; ++a)
         best[a] = group_max<G>(best[a], gl, lane);
+      if (kExtras && has_dbg_cand[p] && r < F->dbg_nrows)
+      {
+        // verbose dumps: what compute_nw_row() leaves behind for EVERY candidate base (ram_extend.c:1006-1039)
+        const bool open = (r - B + K0 >= S.tmin) && (r - B + K0 + C - 1 <= S.tmax) && (nreal == C);
+        const RowDbg nodbg = {nullptr, nullptr, 0, false};
+        const int n_ext = F->n_ext;
+#pragma unroll 1
+        for (int a = 0; a < 4; ++a)
+        {
+          int nob = 0, noi = 0, noh = 0;
+          const int agg = exact_pass<C, false, false>(S.Pp, S.Dd, S.win, lutb, a, go, ge, (gl == 0) ? kNeg : kNegInf,
+                                                      gl, W, B, r, S.tmin, S.tmax, nob, 0, noi, noh, nodbg);
+          const int hin = carry_scan_exact<C, G>(agg, open, ge, gl);
+          const int bv = sel4(a, best[0], best[1], best[2], best[3]);
+          int idx = kBig, gf = -2147483647, gla = -2147483647;
+          int *cells = (F->dbg_cells != nullptr && S.valid)
+                           ? F->dbg_cells + (((size_t) r * n_ext + S.inst) * 4 + a) * (size_t) W * 2
+                           : nullptr;
+          probe_pass<C>(S.Pp, S.Dd, S.win, lutb, a, go, ge, hin, gl, W, B, r, S.tmin, S.tmax, bv, idx, gf, gla, cells);
+          int kidx = (idx < kBig) ? K0 + idx : kBig;
+          kidx = group_min<G>(kidx, gl, lane);
+          gf = group_max<G>(gf, gl, lane);
+          gla = group_max<G>(gla, gl, lane);
+          if (S.valid && gl == 0)
+          {
+            int *o = F->dbg_cand + (((size_t) r * n_ext + S.inst) * 4 + a) * 3;
+            o[0] = r - B + kidx;
+            o[1] = gf;
+            o[2] = gla;
+          }
+        }
+      }
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a)

@@ -133,6 +133,7 @@ struct ramcu_job
   unsigned char *d_dbg_path = nullptr;   // -outmat mode (negative dbg_rows in job_create_impl)
   int *d_dbg_idx = nullptr;
   int *d_seed_rows = nullptr;   // seed extension: [L][n_ext][2]
+  int *d_dbg_cand = nullptr, *d_dbg_cells = nullptr;   // verbose dumps (ramcu_extend_verbose)
   long long *d_dbg_wait = nullptr;   // RAMCU_STATS=1 diagnostics
   const KernelCfg *ran_cfg = nullptr;
   int ran_passes = 1;         // passes per thread of the launch that ran the job
@@ -538,11 +539,20 @@ static bool plan_solo(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ext,
   }
   // RAMCU_DUO_SPREAD (tuning aid): from how many warps per pass, in per cent of the SM count (0 = never)
   static const int spread_from = getenv("RAMCU_DUO_SPREAD") ? atoi(getenv("RAMCU_DUO_SPREAD")) : 100;
+  // RAMCU_DUO_CTA_WARPS (tuning aid): CTA size, in warps, of the two single-pass layouts below (0 = the default, 2)
+  static const int duo_cta_warps = getenv("RAMCU_DUO_CTA_WARPS") ? atoi(getenv("RAMCU_DUO_CTA_WARPS")) : 0;
   if (duo && spread_from > 0 && warps >= (long long) spread_from * sm / 100 && warps <= (long long) sm * 4)
   {
-    // both passes on every SM: a CTA of each pass per SM, so that each SM has the other pass's rows to compute
-    // while one pass's column sums travel (config 4: 18.5 -> 17.3 ms against 4-warp CTAs on distinct SMs, where
-    // most SMs hold one pass only)
+    // both passes on every SM: small CTAs of FULL warps, so that the block scheduler spreads both passes over
+    // all SMs and each SM has the other pass's rows to compute while one pass's column sums travel. Config 4
+    // (313 warps per pass): 157 CTAs of 2 warps per pass 16.8 ms; one 3-warp CTA of each pass per SM (the third
+    // warp holds 4 of the CTA's 68 instances but costs a whole warp's instructions) 17.3 ms; 4-warp CTAs on
+    // distinct SMs, where most SMs hold one pass only, 18.5 ms.
+    const int w = duo_cta_warps > 0 ? duo_cta_warps : 2;
+    p->n_ctas = (int) ((warps + w - 1) / w);
+    p->threads = cta_threads(n_ext, p->n_ctas, k->G);
+    if (p->threads <= maxt_of(k, np) && (long long) units * p->n_ctas <= (long long) ctas_per_sm(k, np, p->threads) * sm)
+      return true;
     p->n_ctas = sm;
     p->threads = cta_threads(n_ext, p->n_ctas, k->G);
     if (p->threads <= maxt_of(k, np) && ctas_per_sm(k, np, p->threads) >= 2)
@@ -713,7 +723,8 @@ static void pinned_put(ramcu_ctx *c, void *p, size_t cap)
 static void free_job_device(ramcu_ctx *c, ramcu_job *j)
 {
   void *ptrs[] = {j->d_inst, j->d_out, j->d_slots, j->d_fam, j->d_cta_fam, j->d_forced, j->d_dbg_rows,
-                  j->d_dbg_best, j->d_dbg_sums, j->d_dbg_wait, j->d_dbg_path, j->d_dbg_idx, j->d_seed_rows};
+                  j->d_dbg_best, j->d_dbg_sums, j->d_dbg_wait, j->d_dbg_path, j->d_dbg_idx, j->d_seed_rows,
+                  j->d_dbg_cand, j->d_dbg_cells};
   for (void *p : ptrs)
     if (p)
     {
@@ -755,7 +766,8 @@ static void destroy_job(ramcu_ctx *c, ramcu_job *j)
 static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
                            const ramcu_core_t *cores, const ramcu_scoring_t *sc,
                            const ramcu_params_t *pr, int dbg_rows, const uint8_t *forced,
-                           ramcu_job **out, const int32_t *n_row = nullptr, bool duo = false)
+                           ramcu_job **out, const int32_t *n_row = nullptr, bool duo = false,
+                           int verbose_rows = 0, bool verbose_cells = false)
 {
   if (!c || !lib || !sc || !pr || !out || (n_cores > 0 && !cores))
     return fail(RAMCU_ERR_ARG, "ramcu_job_create: NULL argument");
@@ -800,7 +812,7 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
   if (j->n_ext > 0 && pr->L > 0)
   {
     // which outputs are asked for is known from the arguments: lay the job out for the kernel variant it will run
-    j->extras = dbg_rows != 0 || forced != nullptr || getenv("RAMCU_STATS") != nullptr;
+    j->extras = dbg_rows != 0 || forced != nullptr || verbose_rows > 0 || getenv("RAMCU_STATS") != nullptr;
     j->cfg = pick_cfg(c, j->extras ? 2 : 0, B, j->n_ext, pr->lanes_per_instance, pr->concurrent_instances, pr->cta_thread_limit,
                       &j->solo, &j->batch_ctas, duo, &j->plan_cost);
     if (!j->cfg)
@@ -839,6 +851,15 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
       CKJ(cudaMemsetAsync(j->d_dbg_idx, 0, rows * j->n_ext * sizeof(int), c->stream));
       CKJ(cudaMallocAsync(&j->d_dbg_best, rows * j->n_ext * 4 * sizeof(int), c->stream));
       CKJ(cudaMallocAsync(&j->d_dbg_sums, rows * 4 * sizeof(int), c->stream));
+    }
+    if (verbose_rows > 0)   // verbose dumps: per-candidate row values of the first verbose_rows rows
+    {
+      const size_t rows = (size_t) verbose_rows;
+      CKJ(cudaMallocAsync(&j->d_dbg_cand, rows * j->n_ext * 12 * sizeof(int), c->stream));
+      CKJ(cudaMallocAsync(&j->d_dbg_best, rows * j->n_ext * 4 * sizeof(int), c->stream));
+      CKJ(cudaMallocAsync(&j->d_dbg_sums, rows * 4 * sizeof(int), c->stream));
+      if (verbose_cells)
+        CKJ(cudaMallocAsync(&j->d_dbg_cells, rows * j->n_ext * 4 * W * 2 * sizeof(int), c->stream));
     }
     if (dbg_rows == 0 && forced)   // seed extension: the query is the consensus, row values come back
     {
@@ -883,6 +904,9 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     f.dbg_best = j->d_dbg_best;
     f.dbg_sums = j->d_dbg_sums;
     f.seed_rows = j->d_seed_rows;
+    f.dbg_cand = j->d_dbg_cand;
+    f.dbg_cells = j->d_dbg_cells;
+    f.dbg_nrows = verbose_rows;
     if (n_row)
       for (int code = 0; code < RAMCU_NCODES; ++code)
         f.mN[code] = n_row[code];
@@ -1645,6 +1669,71 @@ extern "C" int ramcu_extend_paths(ramcu_ctx *c, ramcu_library *lib, int directio
         memcpy(path_state_out + (r * (size_t) n_cores + i) * W, path.data() + (r * ne + e) * W, W);
         row_best_out[r * (size_t) n_cores + i] = best[(r * ne + e) * 4 + (cons[r] & 3)];
         row_best_idx_out[r * (size_t) n_cores + i] = idx[r * ne + e];
+      }
+  }
+  ramcu_job_free(c, j);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// VERBOSE >= 10 dumps: one extend_alignment() call that also reports what compute_nw_row() returned and
+// left behind for EVERY candidate base of every processed row (ram_extend.c:992-1090, 1139-1141)
+// ------------------------------------------------------------------------------------------
+extern "C" int ramcu_extend_verbose(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
+                                    const ramcu_core_t *cores, const ramcu_scoring_t *sc,
+                                    const ramcu_params_t *pr, uint8_t *master_out, int32_t *ext_len_out,
+                                    int32_t *score_add_out, ramcu_result_t *res, int n_rows, int32_t *cand_out,
+                                    int32_t *sums_out, int32_t *cells_out)
+{
+  if (!pr || !cand_out || !sums_out || n_rows < 0)
+    return fail(RAMCU_ERR_ARG, "ramcu_extend_verbose: bad argument");
+  if (pr->L <= 0 || n_cores <= 0 || n_rows == 0)
+    return ramcu_extend(c, lib, direction, n_cores, cores, sc, pr, master_out, ext_len_out, score_add_out, res);
+  const size_t W = 2 * (size_t) pr->bandwidth + 1;
+  const size_t per_row = (size_t) n_cores * (cells_out ? 4 * W * 2 + 16 : 16) * sizeof(int);
+  if ((size_t) n_rows * per_row > ((size_t) 16 << 30))
+    return fail(RAMCU_ERR_UNSUPPORTED, "ramcu_extend_verbose: %d rows x %d cores = %zu bytes of dump state (limit 16 GiB)",
+                n_rows, n_cores, (size_t) n_rows * per_row);
+  ramcu_job *j = nullptr;
+  int rc = job_create_impl(c, lib, direction, n_cores, cores, sc, pr, 0, nullptr, &j, nullptr, false, n_rows,
+                           cells_out != nullptr);
+  if (rc)
+    return rc;
+  if (j->n_ctas > 0)
+    rc = ramcu_job_run(c, j);
+  ramcu_result_t r0;
+  if (!rc)
+    rc = ramcu_job_fetch(c, j, master_out, ext_len_out, score_add_out, &r0);
+  if (!rc && res)
+    *res = r0;
+  if (!rc && j->n_ctas > 0 && r0.rows_processed > 0)
+  {
+    const size_t rows = (size_t) std::min(r0.rows_processed, n_rows), ne = (size_t) j->n_ext;
+    std::vector<int> cand(rows * ne * 12), best(rows * ne * 4);
+    CK(cudaMemcpy(cand.data(), j->d_dbg_cand, cand.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(best.data(), j->d_dbg_best, best.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sums_out, j->d_dbg_sums, rows * 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> cells;
+    if (cells_out)
+    {
+      cells.resize(rows * ne * 4 * W * 2);
+      CK(cudaMemcpy(cells.data(), j->d_dbg_cells, cells.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    for (size_t r = 0; r < rows; ++r)
+      for (size_t e = 0; e < ne; ++e)
+      {
+        const size_t i = (size_t) j->orig[e];
+        for (int a = 0; a < 4; ++a)
+        {
+          int32_t *o = cand_out + ((r * (size_t) n_cores + i) * 4 + a) * 4;
+          o[0] = best[(r * ne + e) * 4 + a];
+          o[1] = cand[((r * ne + e) * 4 + a) * 3];
+          o[2] = cand[((r * ne + e) * 4 + a) * 3 + 1];
+          o[3] = cand[((r * ne + e) * 4 + a) * 3 + 2];
+        }
+        if (cells_out)
+          memcpy(cells_out + (r * (size_t) n_cores + i) * 4 * W * 2, cells.data() + (r * ne + e) * 4 * W * 2,
+                 4 * W * 2 * sizeof(int));
       }
   }
   ramcu_job_free(c, j);

@@ -152,6 +152,205 @@ ramx_boundary_context(void)
   return g_ctx;
 }
 
+/* reference host function (report.c:19-20), linked unchanged */
+void printExtensionRegion(struct coreAlignment *currCore, int direction, int row, int capped,
+                          struct sequenceLibrary *seqLib);
+
+/*
+ * -vvvv / -vvvvv / -vvvvvv (VERBOSE 10 / 12 / 20): the per-row dumps of the reference's column loop
+ * (ram_extend.c:949-959, 992-1090, 1177-1214; bnw_extend.c:843-868), printed in the reference's order
+ * from what the kernel reports for every candidate base of every processed row (ramcu_extend_verbose):
+ * row best and its column, the gap values of the two edge cells, the column sums and -- from -vvvvv --
+ * every band cell. The only arithmetic done here is the bookkeeping the prints themselves show
+ * (clamp / cap of a printed score, the record setter, the improvement rule); no DP.
+ */
+static void
+print_verbose_rows(int direction, struct coreAlignment *coreAlign, struct sequenceLibrary *seqLib, int n,
+                   int BANDWIDTH, int CAPPENALTY, int MINIMPROVEMENT, int rows, const uint8_t *cons,
+                   const int32_t *cand, const int32_t *sums, const int32_t *cells)
+{
+  const size_t W = 2 * (size_t) BANDWIDTH + 1;
+  int *high = (int *) calloc(n > 0 ? n : 1, sizeof(int));
+  int max_ext = 0, max_row = -1;
+  int r, i, offset;
+  struct coreAlignment *c;
+  if (!high)
+  {
+    printf("extend_alignment: Error could not allocate memory for the verbose dumps\n");
+    exit(1);
+  }
+  for (r = 0; r < rows; r++)
+  {
+    int curr = 0, a;
+    char besta = 0;
+    int totalExtendable = 0, numOutOfSeq = 0, numHighScore = 0;
+    float score_per_position_since_max = 0.0;
+    for (a = 0; a < 4; a++)
+    {
+      i = 0;
+      for (c = coreAlign; c != NULL && i < n; c = c->next, i++)
+      {
+        const int32_t *cd = cand + (((size_t) r * n + i) * 4 + a) * 4;
+        int best = cd[0];
+        if (!((direction && c->rightExtendable) || (!direction && c->leftExtendable)))
+          continue;
+        if (direction)
+          printf("RIGHT ROW %d with '%c': n = %d\n", r, num_to_char((char) a), i);
+        else
+          printf("LEFT ROW %d with '%c': n = %d\n", r, num_to_char((char) a), i);
+        if (VERBOSE > 12 && VERBOSE < 100)
+        {
+          /* the bound tests of compute_nw_row(), bnw_extend.c:778-788, 824-868, for their messages */
+          uint64_t start_seq_pos;
+          if (direction)
+            start_seq_pos = c->orient ? c->rightSeqPos - 1 : c->rightSeqPos + 1;
+          else
+            start_seq_pos = c->orient ? c->leftSeqPos + 1 : c->leftSeqPos - 1;
+          for (offset = -BANDWIDTH; offset <= BANDWIDTH; offset++)
+          {
+            const int seq_offset = ((direction ? 1 : 0) == (c->orient ? 1 : 0)) ? -offset - r : offset + r;
+            const uint64_t seq_idx = start_seq_pos + seq_offset;
+            if (start_seq_pos < (uint64_t) BANDWIDTH && seq_offset < 0 && (uint64_t) abs(seq_offset) > start_seq_pos)
+              printf("Short circuiting right extension n=%d ( start_seq_pos = %ld, "
+                     "seq_offset = %d ) because of lower sequence bound %ld [overflow avoided]\n", i,
+                     (long) start_seq_pos, seq_offset, (long) c->lowerSeqBound);
+            else if (seq_idx > c->upperSeqBound)
+              printf("Short circuiting right extension n=%d ( start_seq_pos = %ld, "
+                     "seq_offset = %d, seq_idx = %ld ) because of upper sequence bound %ld\n", i,
+                     (long) start_seq_pos, seq_offset, (long) seq_idx, (long) c->upperSeqBound);
+            else if (seq_idx < c->lowerSeqBound)
+              printf("Short circuiting right extension n=%d ( start_seq_pos = %ld, "
+                     "seq_offset = %d, seq_idx = %ld ) because of lower sequence bound %ld\n", i,
+                     (long) start_seq_pos, seq_offset, (long) seq_idx, (long) c->lowerSeqBound);
+          }
+        }
+        if (VERBOSE >= 12 && cells != NULL)
+        {
+          const int32_t *cl = cells + (((size_t) r * n + i) * 4 + a) * W * 2;
+          printf("    Gap: ");
+          for (offset = 0; offset < (int) W; offset++)
+            printf(" %d", cl[2 * offset + 1]);
+          printf("\n");
+          printf("    Sub: ");
+          for (offset = 0; offset < (int) W; offset++)
+            printf(" %d", cl[2 * offset]);
+          printf("\n");
+        }
+        if (best < 0)
+          printf("  best score = %d @ column %d -- max(0,best_score) = 0!, prev best score = %d\n", best, cd[1],
+                 high[i]);
+        else
+          printf("  best score = %d @ column %d, prev best score = %d\n", best, cd[1], high[i]);
+        if ((direction && cd[2] < -279000) || (!direction && cd[3] < -279000))
+          printf(" **OUT_OF_SEQ**");
+        if (best < 0)
+          best = 0;
+        if (!(best >= high[i] + CAPPENALTY))
+          printf(" **CAPPED** contributing = %d", high[i] + CAPPENALTY);
+        printf("\n");
+        if (VERBOSE >= 12)
+          printExtensionRegion(c, direction, r, 0, seqLib);
+      }
+      printf("  Total Score for '%c' = %d\n", num_to_char((char) a), sums[(size_t) r * 4 + a]);
+      if (sums[(size_t) r * 4 + a] > curr)
+      {
+        curr = sums[(size_t) r * 4 + a];
+        besta = (char) a;
+      }
+    }
+    if ((uint8_t) besta != cons[r])
+    {
+      printf("extend_alignment: the verbose dump and the extension disagree on row %d\n", r);
+      exit(1);
+    }
+    printf("ROW %d complete, '%c' chosen as the consensus. curr_ext_score = %d\n", r, num_to_char(besta), curr);
+    /* the bookkeeping of the reference's fifth pass (ram_extend.c:1100-1150) */
+    i = 0;
+    for (c = coreAlign; c != NULL && i < n; c = c->next, i++)
+    {
+      const int32_t *cd = cand + (((size_t) r * n + i) * 4 + besta) * 4;
+      if (!((direction && c->rightExtendable) || (!direction && c->leftExtendable)))
+        continue;
+      if ((!direction && cd[2] < -279000) || (direction && cd[3] < -279000))
+        numOutOfSeq++;
+      if (cd[0] > high[i])
+      {
+        high[i] = cd[0];
+        numHighScore++;
+      }
+      totalExtendable++;
+    }
+    if (abs(r - max_row) > 0)
+      score_per_position_since_max = ((float) (curr - max_ext) / abs(r - max_row));
+    printf("Alignment Extension: curr_extension_score = %d, "
+           "max_extension_score = %d @ row %d\n                     "
+           "score_per_position_overall = %0.1f, "
+           "score_per_position_since_max = %0.1f\n"
+           "                     total_edges = %d, num_extending = %d, num_out_of_seq = %d\n",
+           curr, max_ext, max_row, ((float) curr / (r + 1)), score_per_position_since_max, totalExtendable,
+           numHighScore, numOutOfSeq);
+    if (curr >= max_ext + (abs(max_row - r) * MINIMPROVEMENT))
+    {
+      printf("                     **This row is now the new max**\n");
+      max_row = r;
+      max_ext = curr;
+    }
+    else
+      printf("                     extensions since last max score %d\n", abs(r - max_row));
+  }
+  free(high);
+}
+
+/* one extend_alignment() call with the -vvvv.. dumps */
+static void
+run_verbose(int direction, struct coreAlignment *coreAlign, struct sequenceLibrary *seqLib, int n, int N,
+            int BANDWIDTH, int CAPPENALTY, int MINIMPROVEMENT, struct scoringSystem *scoreParams,
+            const ramcu_core_t *cores, const ramcu_scoring_t *scp, const ramcu_params_t *prp, uint8_t *cons,
+            int32_t *ext_len, int32_t *score_add, ramcu_result_t *resp)
+{
+  /* -vvvv and up: a plain run tells how many rows there are, then the run whose results are used also
+   * returns the dump data of exactly those rows */
+  int32_t *cand, *sums, *cells = NULL;
+  size_t rows;
+  ahead_drop();
+  if (VERBOSE >= 12)
+  {
+    /* ram_extend.c:949-959: the boundary row, for all N cores */
+    int i, offset;
+    for (i = 0; i < N; i++)
+    {
+      printf("SW Matrix Boundary Conditions ( n = %d ):\n", i);
+      printf("  GAP: ");
+      for (offset = -BANDWIDTH; offset <= BANDWIDTH; offset++)
+        printf(" %d", offset == 0 ? 0 : abs(offset) * scoreParams->gapextn + scoreParams->gapopen);
+      printf("\n  SUB: ");
+      for (offset = -BANDWIDTH; offset <= BANDWIDTH; offset++)
+        printf(" %d", offset == 0 ? 0 : abs(offset) * scoreParams->gapextn + scoreParams->gapopen);
+      printf("\n");
+    }
+  }
+  if (ramcu_extend(g_ctx, g_lib, direction ? 1 : 0, n, cores, scp, prp, cons, ext_len, score_add, resp) != RAMCU_OK)
+    die("ramcu_extend");
+  rows = (size_t) (resp->rows_processed > 0 ? resp->rows_processed : 1);
+  cand = (int32_t *) calloc(rows * (size_t) (n > 0 ? n : 1) * 16, sizeof(int32_t));
+  sums = (int32_t *) calloc(rows * 4, sizeof(int32_t));
+  if (VERBOSE >= 12)
+    cells = (int32_t *) calloc(rows * (size_t) (n > 0 ? n : 1) * 4 * (2 * (size_t) BANDWIDTH + 1) * 2, sizeof(int32_t));
+  if (!cand || !sums || (VERBOSE >= 12 && !cells))
+  {
+    printf("extend_alignment: Error could not allocate memory for the verbose dumps\n");
+    exit(1);
+  }
+  if (ramcu_extend_verbose(g_ctx, g_lib, direction ? 1 : 0, n, cores, scp, prp, cons, ext_len, score_add, resp,
+                           resp->rows_processed, cand, sums, cells) != RAMCU_OK)
+    die("ramcu_extend_verbose");
+  print_verbose_rows(direction, coreAlign, seqLib, n, BANDWIDTH, CAPPENALTY, MINIMPROVEMENT, resp->rows_processed, cons,
+                     cand, sums, cells);
+  free(cand);
+  free(sums);
+  free(cells);
+}
+
 int
 extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
                  struct sequenceLibrary *seqLib, char *master, int BANDWIDTH, int CAPPENALTY,
@@ -175,13 +374,6 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
     else
       printf("extend_alignment(left): Called with %d edges\n", N);
   }
-  if (VERBOSE >= 10)
-  {
-    /* per-row dumps of every DP row (-vvvv..) are debug paths of the CPU loop */
-    printf("RAMExtend (CUDA build): -vvvv/-vvvvv/-vvvvvv are not available on the GPU path\n");
-    exit(1);
-  }
-
   const int timing = getenv("RAMX_TIMING") != NULL;
   double t0 = now_s();
   int handled = 0;
@@ -235,7 +427,7 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
   pr.L = L;
   pr.when_to_stop = WHEN_TO_STOP;
 
-  if (ramx_extend_hook != NULL && pathStringFile == NULL)
+  if (ramx_extend_hook != NULL && pathStringFile == NULL && VERBOSE < 10)
     handled = ramx_extend_hook(direction ? 1 : 0, n, cores, &sc, &pr, seqLib, cons, ext_len, score_add, &res);
   if (!handled)
     ensure_library(seqLib);
@@ -298,7 +490,13 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
     free(rbest);
     free(ridx);
     free(path);
+    if (VERBOSE >= 10)   /* -outmat together with -vvvv..: the dumps go to stdout, same results */
+      run_verbose(direction, coreAlign, seqLib, n, N, BANDWIDTH, CAPPENALTY, MINIMPROVEMENT, scoreParams, cores, &sc, &pr,
+                  cons, ext_len, score_add, &res);
   }
+  else if (VERBOSE >= 10)
+    run_verbose(direction, coreAlign, seqLib, n, N, BANDWIDTH, CAPPENALTY, MINIMPROVEMENT, scoreParams, cores, &sc, &pr,
+                cons, ext_len, score_add, &res);
   else
   {
     const char *pe = getenv("RAMCU_PAIR");

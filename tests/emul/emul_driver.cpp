@@ -115,7 +115,9 @@ static int emul_extend_impl(int C, int G, int WS, int threads, const uint8_t *se
                             uint8_t *master_out, int32_t *ext_len_out, int32_t *score_add_out,
                             ramcu_result_t *res, int dbg_nrows, const uint8_t *forced,
                             int32_t *rows_out, int32_t *best_out, int32_t *sums_out,
-                            uint8_t *path_out, int32_t *pbest_out, int32_t *pidx_out)
+                            uint8_t *path_out, int32_t *pbest_out, int32_t *pidx_out,
+                            int verbose_rows = 0, int32_t *cand_out = nullptr, int32_t *vsums_out = nullptr,
+                            int32_t *cells_out = nullptr)
 {
   const Cfg *cfg = nullptr;
   for (const Cfg &c : kCfgs)
@@ -196,10 +198,26 @@ static int emul_extend_impl(int C, int G, int WS, int threads, const uint8_t *se
     f.dbg_best = dbest.data();
     f.dbg_sums = dsums.data();
   }
+  std::vector<int> dcand, dcells;
+  if (verbose_rows > 0)   // verbose dumps (ramcu_extend_verbose)
+  {
+    dcand.assign((size_t) verbose_rows * n_ext * 12, 0);
+    dbest.assign((size_t) verbose_rows * n_ext * 4, 0);
+    dsums.assign((size_t) verbose_rows * 4, 0);
+    f.dbg_cand = dcand.data();
+    f.dbg_best = dbest.data();
+    f.dbg_sums = dsums.data();
+    f.dbg_nrows = verbose_rows;
+    if (cells_out)
+    {
+      dcells.assign((size_t) verbose_rows * n_ext * 4 * W * 2, 0);
+      f.dbg_cells = dcells.data();
+    }
+  }
   int ticket = 0;
   LaunchArgs a = {};
   // as in ramcu.cu: the lean instantiation unless a diagnostic / per-row output is asked for
-  a.fn = (f.forced || f.dbg_rows || f.dbg_best || f.dbg_path || f.seed_rows) ? cfg->fnx : cfg->fn;
+  a.fn = (f.forced || f.dbg_rows || f.dbg_best || f.dbg_path || f.seed_rows || f.dbg_cand) ? cfg->fnx : cfg->fn;
   a.fams = &f;
   a.cta_fam = cta_fam.data();
   a.ticket = &ticket;
@@ -223,6 +241,23 @@ static int emul_extend_impl(int C, int G, int WS, int threads, const uint8_t *se
         pbest_out[(size_t) r * n_cores + orig[e]] = dbest[((size_t) r * n_ext + e) * 4 + (master[r] & 3)];
         pidx_out[(size_t) r * n_cores + orig[e]] = didx[(size_t) r * n_ext + e];
       }
+  for (int r = 0; r < std::min(verbose_rows, result[1]); ++r)
+  {
+    for (int e = 0; e < n_ext; ++e)
+    {
+      for (int a4 = 0; a4 < 4; ++a4)
+      {
+        int32_t *o = cand_out + (((size_t) r * n_cores + orig[e]) * 4 + a4) * 4;
+        o[0] = dbest[((size_t) r * n_ext + e) * 4 + a4];
+        for (int q = 0; q < 3; ++q)
+          o[1 + q] = dcand[(((size_t) r * n_ext + e) * 4 + a4) * 3 + q];
+      }
+      if (cells_out)
+        memcpy(cells_out + ((size_t) r * n_cores + orig[e]) * 4 * W * 2, dcells.data() + ((size_t) r * n_ext + e) * 4 * W * 2,
+               (size_t) 4 * W * 2 * sizeof(int));
+    }
+    memcpy(vsums_out + (size_t) r * 4, dsums.data() + (size_t) r * 4, 4 * sizeof(int));
+  }
   for (int r = 0; r < dbg_nrows; ++r)
   {
     for (int e = 0; e < n_ext; ++e)
@@ -262,6 +297,19 @@ extern "C" int emul_extend_paths(int C, int G, int WS, int threads, const uint8_
   return emul_extend_impl(C, G, WS, threads, seq, seq_len, direction, n_cores, cores, sc, pr, master_out,
                           ext_len_out, score_add_out, res, 0, nullptr, nullptr, nullptr, nullptr, path_out,
                           pbest_out, pidx_out);
+}
+
+// Same contract as ramcu_extend_verbose() (include/ramcu.h)
+extern "C" int emul_extend_verbose(int C, int G, int WS, int threads, const uint8_t *seq, uint64_t seq_len,
+                                   int direction, int n_cores, const ramcu_core_t *cores,
+                                   const ramcu_scoring_t *sc, const ramcu_params_t *pr,
+                                   uint8_t *master_out, int32_t *ext_len_out, int32_t *score_add_out,
+                                   ramcu_result_t *res, int n_rows, int32_t *cand_out, int32_t *sums_out,
+                                   int32_t *cells_out)
+{
+  return emul_extend_impl(C, G, WS, threads, seq, seq_len, direction, n_cores, cores, sc, pr, master_out,
+                          ext_len_out, score_add_out, res, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, n_rows, cand_out, sums_out, cells_out);
 }
 
 // Same contract as the device part of ramcu_library_from_twobit() (include/ramcu.h): 2bit packed DNA

@@ -217,6 +217,8 @@ class Emulator:
                                          vp, vp, vp, P(ExtendResult), vp, vp, vp, P(ExtendResult)]
         lib.emul_extend_paths.argtypes = [i32, i32, i32, i32, vp, u64, i32, i32, vp, P(Scoring), P(Params),
                                           vp, vp, vp, P(ExtendResult), vp, vp, vp]
+        lib.emul_extend_verbose.argtypes = [i32, i32, i32, i32, vp, u64, i32, i32, vp, P(Scoring), P(Params),
+                                            vp, vp, vp, P(ExtendResult), i32, vp, vp, vp]
 
     def configs(self):
         out = []
@@ -302,6 +304,65 @@ def emul_extend_paths(emul, cfg, direction, cores, seq, sc, p, threads=128):
     rp = res.rows_processed
     return dict(rows_processed=rp, extended_bp=res.extended_bp, master=master[:rp].copy(), state=state[:rp],
                 best=best[:rp], idx=idx[:rp])
+
+
+def emul_extend_verbose(emul, cfg, direction, cores, seq, sc, p, n_rows, cells=False, threads=128):
+    """ramcu_extend_verbose through the CPU emulation of the kernel source"""
+    cores = np.ascontiguousarray(cores, dtype=CORE_DTYPE)
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    n, W, L = cores.size, 2 * p.bandwidth + 1, max(p.L, 1)
+    master = np.zeros(L + 1, dtype=np.uint8)
+    ext_len = np.zeros(n, dtype=np.int32)
+    score_add = np.zeros(n, dtype=np.int32)
+    cand = np.zeros((n_rows, n, 4, 4), dtype=np.int32)
+    sums = np.zeros((n_rows, 4), dtype=np.int32)
+    cel = np.zeros((n_rows, n, 4, W, 2), dtype=np.int32) if cells else None
+    res = ExtendResult()
+    rc = emul.lib.emul_extend_verbose(cfg[0], cfg[1], cfg[2], threads, seq.ctypes.data, seq.size, direction, n,
+                                      cores.ctypes.data, C.byref(sc), C.byref(p), master.ctypes.data,
+                                      ext_len.ctypes.data, score_add.ctypes.data, C.byref(res), n_rows,
+                                      cand.ctypes.data, sums.ctypes.data, cel.ctypes.data if cells else None)
+    assert rc == 0, f"emul_extend_verbose rc={rc}"
+    rp = res.rows_processed
+    return dict(rows_processed=rp, extended_bp=res.extended_bp, master=master[:rp].copy(), cand=cand[:rp],
+                sums=sums[:rp], cells=(cel[:rp] if cells else None))
+
+
+def parse_verbose_dump(text):
+    """The per-candidate values in a RAMExtend -vvvv / -vvvvv stdout (ram_extend.c:992-1090): for each direction
+    a dict (row, base, n) -> dict(best, col, oos, gap, sub) and a dict (row, base) -> column sum."""
+    import re
+    out = {1: ({}, {}), 0: ({}, {})}
+    cur = None
+    row_re = re.compile(r"^(RIGHT|LEFT) ROW (\d+) with '([ACGT])': n = (\d+)$")
+    best_re = re.compile(r"^  best score = (-?\d+) @ column (-?\d+)")
+    tot_re = re.compile(r"^  Total Score for '([ACGT])' = (-?\d+)$")
+    d = None
+    for line in text.splitlines():
+        m = row_re.match(line)
+        if m:
+            d = 1 if m.group(1) == "RIGHT" else 0
+            cur = dict(oos=False)
+            out[d][0][(int(m.group(2)), "ACGT".index(m.group(3)), int(m.group(4)))] = cur
+            last_row = int(m.group(2))
+            continue
+        if cur is not None:
+            if line.startswith("    Gap: "):
+                cur["gap"] = [int(x) for x in line[9:].split()]
+                continue
+            if line.startswith("    Sub: "):
+                cur["sub"] = [int(x) for x in line[9:].split()]
+                continue
+            m = best_re.match(line)
+            if m:
+                cur["best"], cur["col"] = int(m.group(1)), int(m.group(2))
+                continue
+            if "**OUT_OF_SEQ**" in line:
+                cur["oos"] = True
+        m = tot_re.match(line)
+        if m and d is not None:
+            out[d][1][(last_row, "ACGT".index(m.group(1)))] = int(m.group(2))
+    return out
 
 
 def format_outmat(direction, cores, seq, bandwidth, master, state, best, idx):

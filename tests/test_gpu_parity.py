@@ -362,6 +362,38 @@ def test_cli_outmat_byte_identical(name, tmp_path):
     assert (tmp_path / "cons.fa").read_text() == case["want"]["cons.fa"]
 
 
+@pytest.mark.parametrize("name,level", [("config1_default", "-vvvv"), ("config1_default", "-vvvvv"),
+                                        ("config1_default", "-vvvvvv"), ("satellite", "-vvvv"),
+                                        ("satellite", "-vvvvvv"), ("overlap", "-vvvv"), ("tandem", "-vvvvv")])
+def test_cli_verbose_dumps_byte_identical(name, level, tmp_path):
+    """-vvvv / -vvvvv / -vvvvvv (VERBOSE 10 / 12 / 20): the per-row dumps of the reference's column loop
+    (ram_extend.c:949-959, 992-1090, 1177-1214; bnw_extend.c:843-868), printed by the boundary from what the
+    kernel reports for every candidate base, against the reference binary's stdout (sha256, line count,
+    first and last lines; tests/golden/make_golden_verbose.py)."""
+    import hashlib
+    import json
+    exe = os.path.join(ROOT, "repeatafterme_b200", "bin", "RAMExtend")
+    if not os.path.exists(exe):
+        pytest.skip("bin/RAMExtend not built (needs the reference's host objects)")
+    from tests.cases import filter_stdout
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", f"cli_{name}", "verbose.json")))[level]
+    case = gio.load_cli(name)
+    tb, rg = str(tmp_path / "in.2bit"), str(tmp_path / "in.tsv")
+    synth.write_twobit(tb, case["names"], case["seqs"])
+    synth.write_ranges(rg, case["bed"])
+    cmd = [exe, "-twobit", tb, "-ranges", rg, "-cons", str(tmp_path / "cons.fa")] + case["flags"] + [level]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr
+    text = filter_stdout(r.stdout, str(tmp_path))
+    lines = text.splitlines()
+    for i, (a, b) in enumerate(zip(lines[:60], want["head"])):
+        assert a == b, f"line {i}"
+    assert len(lines) == want["lines"]
+    assert lines[-60:] == want["tail"]
+    assert hashlib.sha256(text.encode()).hexdigest() == want["sha256"]
+    assert (tmp_path / "cons.fa").read_text() == case["want"]["cons.fa"]
+
+
 @pytest.fixture(scope="module")
 def ce10_standin(tmp_path_factory):
     from tests import ce10_standin as cs

@@ -187,3 +187,43 @@ def test_emul_two_passes_in_the_same_threads(emul, oracle, cfg, B, threads, n):
     for d, g in zip((1, 0), got):
         want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
         support.compare_extend(want, g, f"cfg={cfg} dir={d}")
+
+
+@pytest.mark.parametrize("name,level,cfg", [("config1_default", "-vvvvv", (8, 4, 29)), ("config1_default", "-vvvvv", (29, 1, 29)),
+                                             ("satellite", "-vvvv", (10, 3, 29)), ("satellite", "-vvvv", (15, 2, 29))])
+def test_emul_verbose_dumps(emul, oracle, name, level, cfg):
+    """VERBOSE >= 10 dumps (ram_extend.c:992-1090): what the kernel reports for EVERY candidate base of every
+    row (row best, its column, the gap values behind **OUT_OF_SEQ**, column sums and -- -vvvvv -- every band
+    cell) == the values in the reference binary's own -vvvv / -vvvvv stdout (tests/golden/cli_*/verbose*.txt.xz,
+    made by tests/golden/make_golden_verbose.py)."""
+    import lzma
+    import os
+    if cfg not in emul.configs():
+        pytest.skip("tiling not in the emulator build")
+    path = os.path.join(os.path.dirname(__file__), "golden", f"cli_{name}", f"verbose{level}.txt.xz")
+    want = support.parse_verbose_dump(lzma.open(path).read().decode())
+    case = gio.load_flat({"config1_default": "config1_default", "satellite": "satellite"}[name])
+    sc = gio.oracle_scoring_for(case, oracle).to_product()
+    p = gio.params_for(case)
+    cells = level != "-vvvv"
+    W = 2 * p.bandwidth + 1
+    for d in (1, 0):
+        plain = emul.extend(cfg, d, case["cores"], case["sequence"], sc, p, threads=64)
+        got = support.emul_extend_verbose(emul, cfg, d, case["cores"], case["sequence"], sc, p,
+                                          plain["rows_processed"], cells=cells, threads=64)
+        gio.check_against_golden(case, d, got | dict(ext_len=plain["ext_len"], score_add=plain["score_add"]), f"{name} dir={d}")
+        per, sums = want[d]
+        assert len(sums) == 4 * got["rows_processed"]
+        n_seen = 0
+        for (r, a, n), w in per.items():
+            c = got["cand"][r, n, a]
+            assert (int(c[0]), int(c[1])) == (w["best"], w["col"]), (d, r, a, n)
+            assert (int(c[2] if d else c[3]) < -279000) == w["oos"], (d, r, a, n)
+            if cells:
+                assert got["cells"][r, n, a, :, 1].tolist() == w["gap"], (d, r, a, n)
+                assert got["cells"][r, n, a, :, 0].tolist() == w["sub"], (d, r, a, n)
+            n_seen += 1
+        ext = int((case["cores"]["right_extendable" if d else "left_extendable"] != 0).sum())
+        assert n_seen == 4 * ext * got["rows_processed"]
+        for (r, a), s in sums.items():
+            assert int(got["sums"][r, a]) == s, (d, r, a)

@@ -36,13 +36,14 @@ def main(n=10000, flank=5000, reps=3):
         out["product_breakdown"] = [l for l in r.stderr.splitlines() if l.startswith("[ramx timing]")]
         out["product_extended"] = [l for l in r.stdout.splitlines() if l.startswith("Extended")]
         cons = open(os.path.join(tmp, "c.fa")).read()
+        out["consensus_bytes"] = len(cons)
+        print(json.dumps(out), flush=True)     # the product's numbers first: the reference run below may take minutes
         ref_bin = os.path.join(ROOT, "oracle", "_ref", "RAMExtend")
         if os.path.exists(ref_bin) and os.environ.get('CLI_BENCH_REFERENCE'):
             print('reference overhead run', file=sys.stderr, flush=True)
             w, r2 = run(ref_bin, tb, rg, tmp, extra=["-stopafter", "1", "-minimprovement", "100000000"])
             out["reference_host_overhead_wall_s"] = round(w, 3)
-        out["consensus_bytes"] = len(cons)
-    print(json.dumps(out))
+            print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
