@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define RAMCU_ABI_VERSION 2
+#define RAMCU_ABI_VERSION 3
 #define RAMCU_NCODES 5            /* matrix columns: A,C,G,T,N (sequence.h:7-15; 99 -> 4)      */
 #define RAMCU_MAX_BANDWIDTH 1023  /* 2*B+1 <= 2047 band cells: 32 lanes x 64 cells                */
 
@@ -207,12 +207,13 @@ int ramcu_extend_pair(ramcu_ctx *ctx, ramcu_library *lib, int n_cores, const ram
  *   row_best_out[r * n_cores + i]               compute_nw_row()'s return value for the chosen base
  *   row_best_idx_out[r * n_cores + i]           band index of its first best cell
  *                                                (curr_row_best_col_idx - row_idx + BANDWIDTH)
- * with W = 2 * bandwidth + 1; arrays hold params->L rows; entries of other cores are left untouched.
- * Debug path: L x n_cores x W is limited to 4 Gi cells. */
+ * with W = 2 * bandwidth + 1; the arrays hold n_rows rows (rows beyond are not reported: a caller that runs
+ * ramcu_extend() first knows rows_processed and sizes them by that, as csrc/ramx_boundary.c does); entries of other
+ * cores are left untouched. Debug path: n_rows x n_cores x W is limited to 16 Gi cells. */
 int ramcu_extend_paths(ramcu_ctx *ctx, ramcu_library *lib, int direction, int n_cores,
                        const ramcu_core_t *cores, const ramcu_scoring_t *scoring,
                        const ramcu_params_t *params, uint8_t *master_out, int32_t *ext_len_out,
-                       int32_t *score_add_out, ramcu_result_t *res, uint8_t *path_state_out,
+                       int32_t *score_add_out, ramcu_result_t *res, int n_rows, uint8_t *path_state_out,
                        int32_t *row_best_out, int32_t *row_best_idx_out);
 
 /* VERBOSE >= 10 dumps (ram_extend.c:992-1090, 1139-1141, 1177-1214): ramcu_extend() that also returns, for the

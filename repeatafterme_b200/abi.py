@@ -159,7 +159,7 @@ def load_ramcu(path: str = LIB_PATH) -> C.CDLL:
     lib.ramcu_extend_pair.argtypes = [vp, vp, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult),
                                       vp, vp, vp, P(ExtendResult)]
     lib.ramcu_extend_paths.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult),
-                                       vp, vp, vp]
+                                       i32, vp, vp, vp]
     lib.ramcu_extend_verbose.argtypes = [vp, vp, i32, i32, vp, P(Scoring), P(Params), vp, vp, vp, P(ExtendResult),
                                          i32, vp, vp, vp]
     lib.ramcu_seed_extend_batch.argtypes = [vp, vp, i32, vp, P(Scoring), vp, i32, i32, vp]
@@ -284,7 +284,7 @@ class RamCu:
         res = ExtendResult()
         self._check(self.lib.ramcu_extend_paths(self.ctx, lib_h, direction, n, cores.ctypes.data, C.byref(scoring),
                                                 C.byref(params), master.ctypes.data, ext_len.ctypes.data,
-                                                score_add.ctypes.data, C.byref(res), state.ctypes.data,
+                                                score_add.ctypes.data, C.byref(res), L, state.ctypes.data,
                                                 best.ctypes.data, idx.ctypes.data))
         rp = res.rows_processed
         return res, master[:rp].copy(), ext_len, score_add, state[:rp], best[:rp], idx[:rp]

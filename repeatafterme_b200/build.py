@@ -135,9 +135,10 @@ def build_cli(force=False):
 
 def build_emulator():
     """tests/emul/libramemul.so: the kernel source compiled for the CPU (test infrastructure; built
-    here so that a kernel edit that breaks the emulation shim shows up in the build check)"""
+    here so that a kernel edit that breaks the emulation shim shows up in the build check). Built with
+    -DRAMCU_CHECK: every CPU test of the kernel source also runs its index assertions."""
     emul = os.path.join(ROOT, "tests", "emul")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-DRAMCU_EMUL", "-I.", "-fPIC", "-shared", "-pthread",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-DRAMCU_EMUL", "-DRAMCU_CHECK", "-I.", "-fPIC", "-shared", "-pthread",
                            "-o", "libramemul.so", "emul_driver.cpp"], cwd=emul)
     return os.path.join(emul, "libramemul.so")
 

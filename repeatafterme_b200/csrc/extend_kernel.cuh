@@ -38,6 +38,15 @@
 #define RAMCU_SHARED_STRUCT(type, name) __shared__ type name
 #endif
 #include <stdint.h>
+// -DRAMCU_CHECK: a build with in-kernel index assertions (library word indices, instance / CTA indices, row
+// indices of every per-row output); tools/build_variant.sh check "-DRAMCU_CHECK", then the GPU suite under
+// RAMCU_LIB=tools/variants/libramcu_check.so. A failed assertion traps the kernel and the host reports it.
+#ifdef RAMCU_CHECK
+#include <assert.h>
+#define RAMCU_ASSERT(cond) assert(cond)
+#else
+#define RAMCU_ASSERT(cond) ((void) 0)
+#endif
 
 namespace ramcu {
 
@@ -91,7 +100,8 @@ struct FamDev
   int W, go, ge, cap;
   int minimp, L, stop;
   int mate;               // index of the family's other pass in the same launch (two-pass CTAs), or -1
-  int dbg_nrows;          // rows the dbg_cand / dbg_cells arrays hold
+  int dbg_nrows;          // rows the dbg_* arrays hold (rows beyond are not reported)
+  long long lib_len;      // bases in the library (index assertions of the RAMCU_CHECK build)
   int m[8][4];            // m[code][cand]; code 4 = N, 5 = out of bounds (value unused)
   int mN[8];              // mN[code]: score of an N consensus base (forced consensus 4, seed extension)
 };
@@ -168,11 +178,12 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
 // 5 = outside [lower_seq_bound, upper_seq_bound].
 __device__ __forceinline__ int fetch_code(const uint32_t *__restrict__ lib2,
                                           const uint32_t *__restrict__ libn, long long start,
-                                          int sgn, int comp, int tmin, int tmax, int t)
+                                          int sgn, int comp, int tmin, int tmax, int t, const long long lib_len)
 {
   if (t < tmin || t > tmax)
     return 5;
   const long long p = start + (long long) sgn * t;
+  RAMCU_ASSERT(p >= 0 && p < lib_len);
   const uint32_t w = __ldg(lib2 + (p >> 4));
   const uint32_t nm = __ldg(libn + (p >> 5));
   int c = (w >> (2 * ((int) p & 15))) & 3;
@@ -219,7 +230,7 @@ __device__ __forceinline__ uint32_t spread1to4(uint32_t x)
 __device__ __forceinline__ void feed16(const uint32_t *__restrict__ lib2, const uint32_t *__restrict__ libn,
                                        const long long start, const int sgn, const int comp,
                                        const int tmin, const int tmax, const int t0, uint32_t &nlo,
-                                       uint32_t &nhi)
+                                       uint32_t &nhi, const long long lib_len)
 {
   const int lo = min(max(tmin - t0, 0), 16), hi = min(max(tmax - t0 + 1, 0), 16);
   const uint32_t inb = (hi > lo) ? ((0xffffu >> (16 - hi)) & ~((1u << lo) - 1u)) : 0u;
@@ -230,6 +241,9 @@ __device__ __forceinline__ void feed16(const uint32_t *__restrict__ lib2, const 
     // (flatten_cores clips the bounds), the arrays are padded by four words on both sides
     const long long p = (sgn > 0) ? start + t0 : start - t0 - 15;
     const long long w2 = p >> 4, wn = p >> 5;
+    // two words of each array; the arrays are padded by four words on both sides
+    RAMCU_ASSERT(w2 >= -4 && w2 + 1 < ((lib_len + 31) / 32) * 2 + 4);
+    RAMCU_ASSERT(wn >= -4 && wn + 1 < (lib_len + 31) / 32 + 4);
     codes = __funnelshift_r(__ldg(lib2 + w2), __ldg(lib2 + w2 + 1), 2 * (int) (p & 15));
     nm = __funnelshift_r(__ldg(libn + wn), __ldg(libn + wn + 1), (int) (p & 31)) & 0xffffu;
     if (sgn < 0)
@@ -528,6 +542,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
   const int cta = sh.cta;
   const FamDev *__restrict__ F0 = fams + cta_fam[cta];
   const int cta_in_fam = cta - F0->cta0;
+  RAMCU_ASSERT(cta >= 0 && cta < (int) gridDim.x && cta_in_fam >= 0 && cta_in_fam < F0->n_ctas);
   if (threadIdx.x < 8)
   {
     sh.lut[2 * threadIdx.x] = make_int4(F0->m[threadIdx.x][0], F0->m[threadIdx.x][1],
@@ -573,6 +588,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     const int grp = warp * IPW + gw;
     S.valid = S.active && (gw < IPW) && (grp < next - first);
     S.inst = S.valid ? first + grp : max(min(next, n_ext) - 1, 0);   // other lanes shadow an instance
+    RAMCU_ASSERT(S.inst >= 0 && S.inst < n_ext);
     const InstDev I = F->inst[S.inst];
     S.start = I.start;
     S.sgn = I.sgn;
@@ -607,7 +623,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
 #pragma unroll 1
     for (int k = 0; k < C; ++k)
     {
-      const int code = fetch_code(F->lib2, F->libn, I.start, I.sgn, I.comp, S.tmin, S.tmax, K0 + k - B);
+      const int code = fetch_code(F->lib2, F->libn, I.start, I.sgn, I.comp, S.tmin, S.tmax, K0 + k - B, F->lib_len);
       const uint32_t b = (uint32_t) (code << 5) << (8 * (k & 3));
 #pragma unroll
       for (int i = 0; i < CW; ++i)
@@ -762,6 +778,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     PassShared &H = sh.ps[p];
     const int slot = r & 1;
     const bool sender = (warp == 0);
+    RAMCU_ASSERT(r >= 0 && r <= L);   // the exchange area holds L + 1 columns
     if (nwarps > 1)
     {
       if (lane == 0)
@@ -882,9 +899,10 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
     const FamDev *__restrict__ F = Fp[p];
     const int n_ext = F->n_ext;
     if ((r & 15) == 0 && is_last)
-      feed16(F->lib2, F->libn, S.start, S.sgn, S.comp, S.tmin, S.tmax, r - B + G * C, S.nib_lo, S.nib_hi);
+      feed16(F->lib2, F->libn, S.start, S.sgn, S.comp, S.tmin, S.tmax, r - B + G * C, S.nib_lo, S.nib_hi, F->lib_len);
     const bool fast_row = use_fast[p] && (r >= S.r_fast_lo) && (r <= S.r_fast_hi);
     const bool alldead = !dbg_on[p] && !has_seed_rows[p] && (r >= S.r_dead);
+    RAMCU_ASSERT(r >= 0 && r < L);    // master[] and every per-row output hold L rows
 
     // argmax over the four bases (ram_extend.c:973-974, 1081-1085)
     int curr = 0, besta = 0;
@@ -902,7 +920,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       besta = min((int) F->forced[r], 4);   // 4: an N base of a given query (seed extension)
       curr = sel4(besta & 3, sums[0], sums[1], sums[2], sums[3]);
     }
-    if (has_dbg_best[p])
+    if (has_dbg_best[p] && r < F->dbg_nrows)
     {
       if (S.valid && gl == 0)
       {
@@ -1014,8 +1032,9 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
       {
         const bool open = (r - B + K0 >= S.tmin) && (r - B + K0 + C - 1 <= S.tmax) && (nreal == C);
         const RowDbg nodbg = {nullptr, nullptr, 0, false};
-        const RowDbg dbg = {F->dbg_rows ? F->dbg_rows + (size_t) r * n_ext * W * 2 : nullptr,
-                            F->dbg_path ? F->dbg_path + (size_t) r * n_ext * W : nullptr, S.inst, S.valid};
+        const bool drow = r < F->dbg_nrows;   // rows the per-row outputs hold
+        const RowDbg dbg = {(F->dbg_rows && drow) ? F->dbg_rows + (size_t) r * n_ext * W * 2 : nullptr,
+                            (F->dbg_path && drow) ? F->dbg_path + (size_t) r * n_ext * W : nullptr, S.inst, S.valid};
         int nob = 0, noi = 0, h0 = 0;
         const int agg = exact_pass<C, false, false>(S.Pp, S.Dd, S.win, lutb, besta, go, ge, (gl == 0) ? kNeg : kNegInf,
                                                     gl, W, B, r, S.tmin, S.tmax, nob, 0, noi, h0, nodbg);
@@ -1047,7 +1066,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         S.high = bestb;
         S.pos = r - B + kidx;
       }
-      if (has_dbg_path[p] && S.valid && gl == 0)
+      if (has_dbg_path[p] && S.valid && gl == 0 && r < F->dbg_nrows)
         F->dbg_idx[(size_t) r * n_ext + S.inst] = kidx;
       if (has_seed_rows[p] && S.valid && gl == 0)
       {

@@ -46,6 +46,25 @@ static int fail(int code, const char *fmt, ...)
                   __FILE__, __LINE__);                                                   \
   } while (0)
 
+// Runs its function when the scope is left unless it was dismissed: an early `return fail(...)` of CK() then
+// releases what the entry point had allocated so far.
+template <class F>
+struct Unwind
+{
+  F f;
+  bool armed = true;
+  ~Unwind()
+  {
+    if (armed)
+      f();
+  }
+};
+template <class F>
+static Unwind<F> unwind(F f)
+{
+  return Unwind<F>{f};
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel registry: band tilings
 // ------------------------------------------------------------------------------------------
@@ -165,6 +184,7 @@ extern "C" int ramcu_init(int device, ramcu_ctx **out)
     return fail(RAMCU_ERR_ARG, "ramcu_init: device %d out of range (0..%d)", device, n - 1);
   CK(cudaSetDevice(device));
   ramcu_ctx *c = new ramcu_ctx();
+  auto undo = unwind([&]() { ramcu_destroy(c); });
   c->device = device;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
@@ -198,13 +218,11 @@ extern "C" int ramcu_init(int device, ramcu_ctx **out)
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, (const void *) int32_peak_kernel);
     if (e != cudaSuccess)
-    {
-      ramcu_destroy(c);
       return fail(RAMCU_ERR_CUDA,
                   "ramcu_init: kernel image not loadable on this device (built for sm_100a): %s",
                   cudaGetErrorString(e));
-    }
   }
+  undo.armed = false;
   *out = c;
   return RAMCU_OK;
 }
@@ -319,6 +337,7 @@ extern "C" int ramcu_int32_peak(ramcu_ctx *c, double *gops, double *ms_out)
 static int library_pack(ramcu_ctx *c, const uint8_t *d_bytes, uint64_t length, ramcu_library **out)
 {
   ramcu_library *lib = new ramcu_library();
+  auto undo = unwind([&]() { ramcu_library_free(c, lib); });
   lib->length = length;
   const uint64_t n_chunks = (length + 31) / 32;  // 32 bases per chunk
   const size_t pad = 4;                           // words of slack on both sides
@@ -340,6 +359,7 @@ static int library_pack(ramcu_ctx *c, const uint8_t *d_bytes, uint64_t length, r
                                                      n_chunks);
     CK(cudaGetLastError());
   }
+  undo.armed = false;
   *out = lib;
   return RAMCU_OK;
 }
@@ -351,12 +371,23 @@ extern "C" int ramcu_library_upload(ramcu_ctx *c, const uint8_t *seq, uint64_t l
     return fail(RAMCU_ERR_ARG, "ramcu_library_upload: NULL argument");
   CK(cudaSetDevice(c->device));
   uint8_t *d_bytes = nullptr;
+  *out = nullptr;
+  auto undo = unwind([&]() {
+    if (d_bytes)
+      cudaFreeAsync(d_bytes, c->stream);
+    if (*out)
+      ramcu_library_free(c, *out);
+    *out = nullptr;
+  });
   CK(cudaMallocAsync(&d_bytes, length ? length : 1, c->stream));
   CK(cudaMemcpyAsync(d_bytes, seq, length, cudaMemcpyHostToDevice, c->stream));
   int rc = library_pack(c, d_bytes, length, out);
-  CK(cudaFreeAsync(d_bytes, c->stream));
+  if (rc)
+    return rc;
   CK(cudaStreamSynchronize(c->stream));   // the caller may reuse / free its host buffer
-  return rc;
+  cudaFreeAsync(d_bytes, c->stream);
+  undo.armed = false;
+  return RAMCU_OK;
 }
 
 extern "C" int ramcu_library_from_device(ramcu_ctx *c, const uint8_t *d_seq, uint64_t length,
@@ -402,7 +433,15 @@ extern "C" int ramcu_library_from_twobit(ramcu_ctx *c, const uint8_t *blob, uint
   const size_t pad = 4;
   uint8_t *d_blob = nullptr;
   WindowDev *d_win = nullptr;
-  unsigned long long *d_ns = nullptr, *d_nl = nullptr;
+  unsigned long long *d_ns = nullptr, *d_nl = nullptr, *d_slow = nullptr;
+  unsigned int *d_nslow = nullptr;
+  auto undo = unwind([&]() {
+    void *tmp[] = {d_blob, d_win, d_ns, d_nl, d_slow, d_nslow};
+    for (void *t : tmp)
+      if (t)
+        cudaFreeAsync(t, c->stream);
+    ramcu_library_free(c, lib);
+  });
   CK(cudaMallocAsync(&lib->alloc2, (n_chunks * 2 + 2 * pad) * sizeof(uint32_t), c->stream));
   CK(cudaMallocAsync(&lib->allocn, (n_chunks + 2 * pad) * sizeof(uint32_t), c->stream));
   lib->d_lib2 = (uint32_t *) lib->alloc2 + pad;
@@ -423,8 +462,6 @@ extern "C" int ramcu_library_from_twobit(ramcu_ctx *c, const uint8_t *blob, uint
     const unsigned long long want = ((n_chunks + 3) / 4 + 255) / 256;   // one thread per 128 bases
     const int grid = (int) std::min<unsigned long long>(want, (unsigned long long) c->sm_count * 16);
     // groups of 128 bases that are not inside one window: at most one per window boundary + the tail
-    unsigned long long *d_slow = nullptr;
-    unsigned int *d_nslow = nullptr;
     const unsigned int slow_cap = 2u * (unsigned int) n_windows + 8u;
     CK(cudaMallocAsync(&d_slow, (size_t) slow_cap * sizeof(unsigned long long), c->stream));
     CK(cudaMallocAsync(&d_nslow, sizeof(unsigned int), c->stream));
@@ -440,7 +477,9 @@ extern "C" int ramcu_library_from_twobit(ramcu_ctx *c, const uint8_t *blob, uint
       CK(cudaGetLastError());
     }
     CK(cudaFreeAsync(d_slow, c->stream));
+    d_slow = nullptr;
     CK(cudaFreeAsync(d_nslow, c->stream));
+    d_nslow = nullptr;
     // positions past `total` inside the last chunk are N
     if (total & 31)
     {
@@ -456,12 +495,17 @@ extern "C" int ramcu_library_from_twobit(ramcu_ctx *c, const uint8_t *blob, uint
       nmask_ranges_kernel<<<n_nranges, 128, 0, c->stream>>>(d_ns, d_nl, n_nranges, lib->d_libn);
       CK(cudaGetLastError());
       CK(cudaFreeAsync(d_ns, c->stream));
+      d_ns = nullptr;
       CK(cudaFreeAsync(d_nl, c->stream));
+      d_nl = nullptr;
     }
-    CK(cudaFreeAsync(d_blob, c->stream));
-    CK(cudaFreeAsync(d_win, c->stream));
     CK(cudaStreamSynchronize(c->stream));   // the caller may reuse its host buffers
+    CK(cudaFreeAsync(d_blob, c->stream));
+    d_blob = nullptr;
+    CK(cudaFreeAsync(d_win, c->stream));
+    d_win = nullptr;
   }
+  undo.armed = false;
   *out = lib;
   return RAMCU_OK;
 }
@@ -891,6 +935,7 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     f.dbg_wait = j->d_dbg_wait;
     f.lib2 = lib->d_lib2;
     f.libn = lib->d_libn;
+    f.lib_len = (long long) lib->length;
     f.inst = j->d_inst;
     f.result = o;
     f.thigh = o + 8;
@@ -906,7 +951,7 @@ static int job_create_impl(ramcu_ctx *c, ramcu_library *lib, int direction, int 
     f.seed_rows = j->d_seed_rows;
     f.dbg_cand = j->d_dbg_cand;
     f.dbg_cells = j->d_dbg_cells;
-    f.dbg_nrows = verbose_rows;
+    f.dbg_nrows = verbose_rows > 0 ? verbose_rows : std::abs(dbg_rows);
     if (n_row)
       for (int code = 0; code < RAMCU_NCODES; ++code)
         f.mN[code] = n_row[code];
@@ -1631,21 +1676,23 @@ extern "C" int ramcu_global_align(ramcu_ctx *c, ramcu_library *lib, int orient, 
 extern "C" int ramcu_extend_paths(ramcu_ctx *c, ramcu_library *lib, int direction, int n_cores,
                                   const ramcu_core_t *cores, const ramcu_scoring_t *sc,
                                   const ramcu_params_t *pr, uint8_t *master_out, int32_t *ext_len_out,
-                                  int32_t *score_add_out, ramcu_result_t *res, uint8_t *path_state_out,
+                                  int32_t *score_add_out, ramcu_result_t *res, int n_rows, uint8_t *path_state_out,
                                   int32_t *row_best_out, int32_t *row_best_idx_out)
 {
-  if (!pr || !path_state_out || !row_best_out || !row_best_idx_out)
-    return fail(RAMCU_ERR_ARG, "ramcu_extend_paths: NULL argument");
-  if (pr->L <= 0 || n_cores <= 0)
+  if (!pr || !path_state_out || !row_best_out || !row_best_idx_out || n_rows < 0)
+    return fail(RAMCU_ERR_ARG, "ramcu_extend_paths: bad argument");
+  if (pr->L <= 0 || n_cores <= 0 || n_rows == 0)
     return ramcu_extend(c, lib, direction, n_cores, cores, sc, pr, master_out, ext_len_out, score_add_out, res);
+  n_rows = std::min(n_rows, pr->L);
   const size_t W = 2 * (size_t) pr->bandwidth + 1;
-  if ((size_t) pr->L * (size_t) n_cores * W > ((size_t) 4 << 30))
-    return fail(RAMCU_ERR_UNSUPPORTED, "ramcu_extend_paths: L x cores x band = %zu cells of path state (limit 4 Gi)",
-                (size_t) pr->L * (size_t) n_cores * W);
+  if ((size_t) n_rows * (size_t) n_cores * W > ((size_t) 16 << 30))
+    return fail(RAMCU_ERR_UNSUPPORTED, "ramcu_extend_paths: rows x cores x band = %zu cells of path state (limit 16 Gi)",
+                (size_t) n_rows * (size_t) n_cores * W);
   ramcu_job *j = nullptr;
-  int rc = job_create_impl(c, lib, direction, n_cores, cores, sc, pr, -pr->L, nullptr, &j);
+  int rc = job_create_impl(c, lib, direction, n_cores, cores, sc, pr, -n_rows, nullptr, &j);
   if (rc)
     return rc;
+  auto undo = unwind([&]() { ramcu_job_free(c, j); });
   if (j->n_ctas > 0)
     rc = ramcu_job_run(c, j);
   ramcu_result_t r0;
@@ -1655,7 +1702,7 @@ extern "C" int ramcu_extend_paths(ramcu_ctx *c, ramcu_library *lib, int directio
     *res = r0;
   if (!rc && j->n_ctas > 0 && r0.rows_processed > 0)
   {
-    const size_t rows = (size_t) r0.rows_processed, ne = (size_t) j->n_ext;
+    const size_t rows = (size_t) std::min(r0.rows_processed, n_rows), ne = (size_t) j->n_ext;
     std::vector<unsigned char> path(rows * ne * W), cons(rows);
     std::vector<int> best(rows * ne * 4), idx(rows * ne);
     CK(cudaMemcpy(path.data(), j->d_dbg_path, path.size(), cudaMemcpyDeviceToHost));
@@ -1671,8 +1718,7 @@ extern "C" int ramcu_extend_paths(ramcu_ctx *c, ramcu_library *lib, int directio
         row_best_idx_out[r * (size_t) n_cores + i] = idx[r * ne + e];
       }
   }
-  ramcu_job_free(c, j);
-  return rc;
+  return rc;   // the job is released by `undo`
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1699,6 +1745,7 @@ extern "C" int ramcu_extend_verbose(ramcu_ctx *c, ramcu_library *lib, int direct
                            cells_out != nullptr);
   if (rc)
     return rc;
+  auto undo = unwind([&]() { ramcu_job_free(c, j); });
   if (j->n_ctas > 0)
     rc = ramcu_job_run(c, j);
   ramcu_result_t r0;
@@ -1736,8 +1783,7 @@ extern "C" int ramcu_extend_verbose(ramcu_ctx *c, ramcu_library *lib, int direct
                  4 * W * 2 * sizeof(int));
       }
   }
-  ramcu_job_free(c, j);
-  return rc;
+  return rc;   // the job is released by `undo`
 }
 
 // ------------------------------------------------------------------------------------------

@@ -442,19 +442,25 @@ extend_alignment(int direction, struct coreAlignment *coreAlign, int ****score,
     /* -outmat: the kernel also reports the path state of every band cell of every committed row;
      * the lines of ram_extend.c:1122-1132 are written here, in the reference's order */
     const size_t W = 2 * (size_t) BANDWIDTH + 1;
-    const size_t cells = (size_t) (L > 0 ? L : 1) * (size_t) (n > 0 ? n : 1);
-    uint8_t *state = (uint8_t *) calloc(cells * W, 1);
-    int32_t *rbest = (int32_t *) calloc(cells, sizeof(int32_t));
-    int32_t *ridx = (int32_t *) calloc(cells, sizeof(int32_t));
+    size_t cells;
+    uint8_t *state;
+    int32_t *rbest, *ridx;
     char *path = (char *) malloc(W + 1);
+    ahead_drop();
+    /* a plain run tells how many rows there are; the path state is then sized by that, not by L */
+    if (ramcu_extend(g_ctx, g_lib, direction ? 1 : 0, n, cores, &sc, &pr, cons, ext_len, score_add, &res) != RAMCU_OK)
+      die("ramcu_extend");
+    cells = (size_t) (res.rows_processed > 0 ? res.rows_processed : 1) * (size_t) (n > 0 ? n : 1);
+    state = (uint8_t *) calloc(cells * W, 1);
+    rbest = (int32_t *) calloc(cells, sizeof(int32_t));
+    ridx = (int32_t *) calloc(cells, sizeof(int32_t));
     if (!state || !rbest || !ridx || !path)
     {
       printf("extend_alignment: Error could not allocate memory for the path strings\n");
       exit(1);
     }
-    ahead_drop();
     if (ramcu_extend_paths(g_ctx, g_lib, direction ? 1 : 0, n, cores, &sc, &pr, cons, ext_len, score_add,
-                           &res, state, rbest, ridx) != RAMCU_OK)
+                           &res, res.rows_processed, state, rbest, ridx) != RAMCU_OK)
       die("ramcu_extend_paths");
     for (r = 0; r < res.rows_processed; r++)
     {

@@ -169,6 +169,7 @@ static int emul_extend_impl(int C, int G, int WS, int threads, const uint8_t *se
   fill_family(f, sc, &p2, n_ext, n_ctas);
   f.lib2 = a2.data() + 4;
   f.libn = an.data() + 4;
+  f.lib_len = (long long) seq_len;
   f.inst = inst.data();
   f.master = master.data();
   f.thigh = thigh.data();
@@ -184,6 +185,7 @@ static int emul_extend_impl(int C, int G, int WS, int threads, const uint8_t *se
     f.dbg_best = dbest.data();
     f.dbg_sums = dsums.data();
     f.forced = forced;
+    f.dbg_nrows = dbg_nrows;
   }
   std::vector<unsigned char> dpath;
   std::vector<int> didx;
@@ -197,6 +199,7 @@ static int emul_extend_impl(int C, int G, int WS, int threads, const uint8_t *se
     f.dbg_idx = didx.data();
     f.dbg_best = dbest.data();
     f.dbg_sums = dsums.data();
+    f.dbg_nrows = p2.L;
   }
   std::vector<int> dcand, dcells;
   if (verbose_rows > 0)   // verbose dumps (ramcu_extend_verbose)
@@ -405,6 +408,7 @@ extern "C" int emul_extend_pair(int C, int G, int WS, int threads, const uint8_t
     slots[p].assign((size_t) (pr->L + 1) * 4 * kRedStride, 0);
     fill_family(f[p], sc, pr, n_ext, n_ctas);
     f[p].lib2 = a2.data() + 4;
+    f[p].lib_len = (long long) seq_len;
     f[p].libn = an.data() + 4;
     f[p].inst = inst[p].data();
     f[p].master = master[p].data();
@@ -487,6 +491,7 @@ extern "C" int emul_seed_rows(int C, int G, int WS, const uint8_t *seq, uint64_t
     f.mN[code] = n_row[code];
   f.lib2 = a2.data() + 4;
   f.libn = an.data() + 4;
+  f.lib_len = (long long) seq_len;
   f.inst = inst.data();
   f.master = master.data();
   f.thigh = thigh.data();

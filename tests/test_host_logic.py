@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     lib = abi.load_ramcu()
     for name in sorted(declared):
         assert getattr(lib, name) is not None
-    assert lib.ramcu_abi_version() == 2
+    assert lib.ramcu_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header(tmp_path):
