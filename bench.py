@@ -510,7 +510,10 @@ def run_cuda(args):
     cli = None
     if rank == 0 and world == 1 and not args.no_cli and n == WORKLOAD["n"] and flank == WORKLOAD["flank"]:
         torch.cuda.synchronize()
-        cli = cli_leg(fam)
+        try:
+            cli = cli_leg(fam)
+        except Exception as e:          # the leg is informative: never let it take the bench line down
+            cli = {"unavailable": f"{type(e).__name__}: {e}"}
         log(f"[cli] {cli}")
     # the single-family leg is done: release it before the genome-scale round
     for j in jobs:
