@@ -41,6 +41,11 @@
 // -DRAMCU_CHECK: a build with in-kernel index assertions (library word indices, instance / CTA indices, row
 // indices of every per-row output); tools/build_variant.sh check "-DRAMCU_CHECK", then the GPU suite under
 // RAMCU_LIB=tools/variants/libramcu_check.so. A failed assertion traps the kernel and the host reports it.
+// The adds of the sweep go to the FMA pipe (add_fma) unless -DRAMCU_NO_SWEEP_FMA (A/B builds): config 4 16.7 -> 16.4 ms,
+// a 96-family batch 317 -> 315 ms.
+#ifndef RAMCU_NO_SWEEP_FMA
+#define RAMCU_SWEEP_FMA 1
+#endif
 #ifdef RAMCU_CHECK
 #include <assert.h>
 #define RAMCU_ASSERT(cond) assert(cond)
@@ -102,12 +107,20 @@ struct FamDev
   int mate;               // index of the family's other pass in the same launch (two-pass CTAs), or -1
   int dbg_nrows;          // rows the dbg_* arrays hold (rows beyond are not reported)
   long long lib_len;      // bases in the library (index assertions of the RAMCU_CHECK build)
+  int one;                // the constant 1, opaque to the compiler (add_fma)
   int m[8][4];            // m[code][cand]; code 4 = N, 5 = out of bounds (value unused)
   int mN[8];              // mN[code]: score of an N consensus base (forced consensus 4, seed extension)
 };
 
 __device__ __forceinline__ int imax(int a, int b) { return max(a, b); }
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
+// a + b issued on the FMA pipe: a * one + b with a multiplier the compiler cannot see through (ptxas turns a
+// literal 1 back into an add and fuses it with the max). With one warp per scheduler the INT32 ALU pipe (two
+// cycles per warp instruction) is what a row waits for, and the FMA pipe is idle.
+__device__ __forceinline__ int add_fma(int a, int b, int one)
+{
+  return a * one + b;
+}
 __device__ __forceinline__ int sel4(int a, int x0, int x1, int x2, int x3)
 {
   const int lo = (a & 1) ? x1 : x0;
@@ -668,6 +681,28 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         best[a] = kNeg;   // bnw_extend.c:760
       if (fast)
       {
+#ifdef RAMCU_SWEEP_FMA
+        // two cells per step: the adds go to the FMA pipe, one three-input max per candidate to the ALU pipe
+        const int one = F->one;   // 1, but not to the compiler
+#pragma unroll
+        for (int k = 0; k + 1 < C; k += 2)
+        {
+          const int4 m4 = *reinterpret_cast<const int4 *>(lutb + win_byte(S.win[k >> 2], k & 3));
+          const int4 n4 = *reinterpret_cast<const int4 *>(lutb + win_byte(S.win[(k + 1) >> 2], (k + 1) & 3));
+          best[0] = imax3(best[0], add_fma(S.Pp[k], m4.x, one), add_fma(S.Pp[k + 1], n4.x, one));
+          best[1] = imax3(best[1], add_fma(S.Pp[k], m4.y, one), add_fma(S.Pp[k + 1], n4.y, one));
+          best[2] = imax3(best[2], add_fma(S.Pp[k], m4.z, one), add_fma(S.Pp[k + 1], n4.z, one));
+          best[3] = imax3(best[3], add_fma(S.Pp[k], m4.w, one), add_fma(S.Pp[k + 1], n4.w, one));
+        }
+        if (C & 1)
+        {
+          const int4 m4 = *reinterpret_cast<const int4 *>(lutb + win_byte(S.win[(C - 1) >> 2], (C - 1) & 3));
+          best[0] = imax(best[0], S.Pp[C - 1] + m4.x);
+          best[1] = imax(best[1], S.Pp[C - 1] + m4.y);
+          best[2] = imax(best[2], S.Pp[C - 1] + m4.z);
+          best[3] = imax(best[3], S.Pp[C - 1] + m4.w);
+        }
+#else
 #pragma unroll
         for (int k = 0; k < C; ++k)
         {
@@ -677,6 +712,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
           best[2] = imax(best[2], S.Pp[k] + m4.z);
           best[3] = imax(best[3], S.Pp[k] + m4.w);
         }
+#endif
 #pragma unroll
         for (int a = 0; a < 4; ++a)
           best[a] = imax(best[a], S.maxD);
@@ -957,7 +993,7 @@ extend_kernel(const FamDev *__restrict__ fams, const int *__restrict__ cta_fam, 
         {
           const int m = *reinterpret_cast<const int *>(lutb + win_byte(wa[k >> 2], k & 3));
           const int Sv = S.Pp[k] + m;
-          const int y = imax(Sv + goe, S.Dd[k] + ge);
+          const int y = imax(Sv + goe, S.Dd[k] + ge);   // (these adds on the FMA pipe: 16.4 -> 17.5 ms, not kept)
           const int pn = imax3(Sv, S.Dd[k], hprev);
           const int hn = imax(hprev + ge, y);
           S.Pp[k] = pn;

@@ -85,6 +85,7 @@ static inline void fill_family(FamDev &f, const ramcu_scoring_t *sc, const ramcu
   f.L = pr->L;
   f.stop = pr->when_to_stop;
   f.mate = -1;
+  f.one = 1;
   for (int code = 0; code < RAMCU_NCODES; ++code)
     for (int a = 0; a < 4; ++a)
       f.m[code][a] = sc->matrix[a][code];
