@@ -394,6 +394,66 @@ def test_cli_verbose_dumps_byte_identical(name, level, tmp_path):
     assert (tmp_path / "cons.fa").read_text() == case["want"]["cons.fa"]
 
 
+@pytest.mark.parametrize("bandwidth,n,lanes,with_cells", [(40, 900, 0, False), (40, 120, 8, True), (100, 260, 0, False),
+                                                         (23, 500, 0, False), (23, 90, 0, True)])
+def test_verbose_values_consistent_with_the_extension(ramcu, oracle, bandwidth, n, lanes, with_cells):
+    """ramcu_extend_verbose on families that span several CTAs and several lanes per instance (static and
+    runtime-width bands): the per-candidate row bests reproduce the column sums through the reference's clamp /
+    cap rule (ram_extend.c:1042-1062) and record setter (:1140-1150), the chosen base's best and column equal
+    what ramcu_extend_paths reports (-outmat, pinned against the reference binary), and the extension itself is
+    the oracle's."""
+    fam = synth.make_family(500 + n, n, 260, 0.15, one_sided_frac=0.1, n_frac=0.003)
+    osc = oracle.scoring("14p43g")
+    sc = osc.to_product()
+    p = make_params(bandwidth=bandwidth, minimprovement=30, L=600, lanes_per_instance=lanes)
+    lib = ramcu.upload_library(fam.sequence)
+    try:
+        for d in (1, 0):
+            want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+            rows = want["rows_processed"]
+            res, master, ext_len, score_add, cand, sums, cells = ramcu.extend_verbose(lib, d, fam.cores, sc, p, rows, cells=with_cells)
+            support.compare_extend(want, _got(res, master, ext_len, score_add), f"verbose dir={d}")
+            r2, m2, e2, s2, state, pbest, pidx = ramcu.extend_paths(lib, d, fam.cores, sc, p)
+            assert np.array_equal(master, m2)
+            ext = np.flatnonzero(fam.cores["right_extendable" if d else "left_extendable"] != 0)
+            high = np.zeros(fam.cores.size, dtype=np.int64)
+            for r in range(rows):
+                best = cand[r, ext, :, 0].astype(np.int64)                       # [ext, candidate]
+                contrib = np.maximum(np.maximum(best, 0), (high[ext] + p.cappenalty)[:, None])
+                got_sums = contrib.sum(axis=0).astype(np.int64)
+                assert np.array_equal((got_sums & 0xffffffff), sums[r].astype(np.int64) & 0xffffffff), (d, r)
+                a = int(master[r])
+                assert np.array_equal(cand[r, ext, a, 0], pbest[r, ext]), (d, r)
+                assert np.array_equal(cand[r, ext, a, 1], r - bandwidth + pidx[r, ext]), (d, r)
+                if cells is not None:
+                    W = 2 * bandwidth + 1
+                    cell = np.maximum(cells[r, ext, :, :, 0], cells[r, ext, :, :, 1])      # [ext, candidate, W]
+                    assert np.array_equal(cell.max(axis=2), cand[r, ext, :, 0]), (d, r)
+                    first = (cell == cell.max(axis=2, keepdims=True)).argmax(axis=2)
+                    assert np.array_equal(r - bandwidth + first, cand[r, ext, :, 1]), (d, r)
+                    assert np.array_equal(cells[r, ext, :, 0, 1], cand[r, ext, :, 2]), (d, r)
+                    assert np.array_equal(cells[r, ext, :, W - 1, 1], cand[r, ext, :, 3]), (d, r)
+                high[ext] = np.maximum(high[ext], best[:, a])
+    finally:
+        ramcu.free_library(lib)
+
+
+def test_twobit_windows_aliasing_the_blob_tail(ramcu):
+    """many windows that all read the last ~200 bases of an unpadded blob (the windows of a library may alias the
+    same source bytes; every 128-base group of such a window takes the base-by-base route): the bounded slow list
+    does not overflow and the decoded library is right"""
+    from tests.test_kernel_emul import _aliasing_windows
+    for n_windows in (12, 40):
+        blob, wins, total, want = _aliasing_windows(n_windows=n_windows)
+        none = np.zeros(0, dtype=np.uint64)
+        h = ramcu.library_from_twobit(blob, wins, none, none, total)
+        try:
+            a2, an = ramcu.download_library(h, total)
+            assert np.array_equal(_decode_packed(a2, an, total), want)
+        finally:
+            ramcu.free_library(h)
+
+
 @pytest.fixture(scope="module")
 def ce10_standin(tmp_path_factory):
     from tests import ce10_standin as cs

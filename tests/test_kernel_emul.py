@@ -227,3 +227,34 @@ def test_emul_verbose_dumps(emul, oracle, name, level, cfg):
         assert n_seen == 4 * ext * got["rows_processed"]
         for (r, a), s in sums.items():
             assert int(got["sums"][r, a]) == s, (d, r, a)
+
+
+def _aliasing_windows(n_bases=1000, n_windows=12, seed=5):
+    """One unpadded record and many windows that all read the last ~200 bases of the blob (the windows of a
+    library may alias the same source bytes): every 128-base group of such a window is a slow group."""
+    rng = np.random.default_rng(seed)
+    codes = rng.integers(0, 4, n_bases).astype(np.uint8)          # A0 C1 G2 T3
+    blob = synth.pack_twobit_record(codes)
+    wins, dst = [], 0
+    for i in range(n_windows):
+        ln = 150 + int(rng.integers(0, 50))
+        src = n_bases - ln - (i % 5)
+        wins.append((dst, ln, 0, src))
+        dst += ln
+    want = np.concatenate([codes[s: s + ln] for (_, ln, _, s) in wins])
+    return np.ascontiguousarray(blob, dtype=np.uint8), np.array(wins, dtype=np.uint64), dst, want
+
+
+def test_emul_twobit_windows_aliasing_the_blob_tail(emul):
+    """more slow groups than windows (all of them in the last bytes of an unpadded blob): the bounded slow list
+    must not overflow and every base must still be decoded"""
+    import ctypes as C
+    blob, wins, total, want = _aliasing_windows()
+    n_chunks = (total + 31) // 32
+    lib2 = np.zeros(2 * n_chunks, dtype=np.uint32)
+    emul.lib.emul_twobit.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
+    nslow = emul.lib.emul_twobit(blob.ctypes.data, blob.size, wins.ctypes.data, len(wins), total, lib2.ctypes.data)
+    assert nslow >= 0
+    i = np.arange(total)
+    got = (lib2[i >> 4] >> (2 * (i & 15)).astype(np.uint32)) & 3
+    assert np.array_equal(got.astype(np.uint8), want)
