@@ -193,7 +193,7 @@ def cli_leg(fam, runs=2):
     from repeatafterme_b200 import synth
     exe = os.path.join(ROOT, "repeatafterme_b200", "bin", "RAMExtend")
     if not os.path.exists(exe):
-        return {"unavailable": "bin/RAMExtend not built (needs the reference's host objects, oracle/_ref)"}
+        return {"unavailable": "bin/RAMExtend not built (needs the reference sources at build time: host/_refobj)"}
     with tempfile.TemporaryDirectory() as tmp:
         tb, rg = os.path.join(tmp, "f.2bit"), os.path.join(tmp, "f.tsv")
         synth.write_family_files(fam, tb, rg)
