@@ -140,6 +140,32 @@ ramx_boundary_forget_library(void)
   g_lib_len = 0;
 }
 
+/* RAMX_TIMING: where the wall clock of the process goes outside the calls timed above. One handler is registered
+ * when the library is loaded (it runs last, after the CUDA runtime's own exit handler), one after the context
+ * exists (it runs first): the difference is the teardown of the context. */
+static double g_t_start;
+
+static void
+timing_at_exit_first(void)
+{
+  fflush(stdout);
+  fprintf(stderr, "[ramx timing] main() done %.3f s after process start\n", now_s() - g_t_start);
+}
+
+static void
+timing_at_exit_last(void)
+{
+  fprintf(stderr, "[ramx timing] exit handlers done %.3f s after process start\n", now_s() - g_t_start);
+}
+
+__attribute__((constructor)) static void
+timing_init(void)
+{
+  g_t_start = now_s();
+  if (getenv("RAMX_TIMING") != NULL)
+    atexit(timing_at_exit_last);
+}
+
 ramcu_ctx *
 ramx_boundary_context(void)
 {
@@ -148,6 +174,8 @@ ramx_boundary_context(void)
     const char *dev = getenv("RAMCU_DEVICE");
     if (ramcu_init(dev ? atoi(dev) : 0, &g_ctx) != RAMCU_OK)
       die("ramcu_init");
+    if (getenv("RAMX_TIMING") != NULL)
+      atexit(timing_at_exit_first);
   }
   return g_ctx;
 }
