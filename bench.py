@@ -572,7 +572,7 @@ def run_cuda(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
-        tf = "r2_extend_kernel_traffic.json" if args.sequential else "r2_extend_kernel_pair_traffic.json"
+        tf = "r2_extend_kernel_traffic.json" if args.sequential else "r2_final_extend_kernel_duo_traffic.json"
         traffic = json.load(open(os.path.join(ROOT, "profiles", tf)))["dram_bytes_per_launch"]
     except Exception:
         pass
