@@ -1,7 +1,7 @@
 /*
  * ramx_batch.c -- RAMExtendBatch: many RAMExtend runs in one process, on one CUDA context per GPU.
  *
- *     RAMExtendBatch [-gpus N] [-chunk K] <manifest>
+ *     RAMExtendBatch [-gpus N] [-procs P] [-chunk K] <manifest>
  *
  * Replaces what util/extend-stk.pl:365-371 (and a RepeatModeler round) does with one
  * `system("RAMExtend ...")` per family. Every manifest line is the argument list of one RAMExtend
@@ -27,7 +27,10 @@
  *               run again on its own, exactly as the single-family CLI does.
  * -outmat runs and anything else the hook declines go through the boundary's own single-family path.
  * With -gpus N the manifest is split over N worker processes (longest first by ranges-file size x band
- * width), one GPU each; families are independent, nothing is exchanged.
+ * width), one GPU each; families are independent, nothing is exchanged. -procs P starts P workers per GPU:
+ * the record and replay phases are the reference's single-threaded host code (loader, report, output files),
+ * so for many small families the host, not the GPU, sets the pace; P processes overlap their host phases and
+ * take turns on the device (separate contexts are time-sliced, a kernel always has the device to itself).
  * An error that makes the reference's main() call exit() ends the worker that hit it.
  */
 #define _GNU_SOURCE
@@ -313,23 +316,26 @@ process(struct family **fams, int n, int chunk)
 int
 main(int argc, char **argv)
 {
-  int gpus = 1, chunk = 512;
+  int gpus = 1, procs = 1, chunk = 512;
   const char *manifest = NULL;
   for (int i = 1; i < argc; ++i)
   {
     if (strcmp(argv[i], "-gpus") == 0 && i + 1 < argc)
       gpus = atoi(argv[++i]);
+    else if (strcmp(argv[i], "-procs") == 0 && i + 1 < argc)
+      procs = atoi(argv[++i]);
     else if (strcmp(argv[i], "-chunk") == 0 && i + 1 < argc)
       chunk = atoi(argv[++i]);
     else
       manifest = argv[i];
   }
-  if (manifest == NULL || gpus < 1 || chunk < 1)
+  if (manifest == NULL || gpus < 1 || procs < 1 || chunk < 1)
   {
-    fprintf(stderr, "usage: RAMExtendBatch [-gpus N] [-chunk K] <manifest>\n"
+    fprintf(stderr, "usage: RAMExtendBatch [-gpus N] [-procs P] [-chunk K] <manifest>\n"
             "  manifest: one RAMExtend argument list per line, optionally preceded by stdout=<file>\n");
     return 1;
   }
+  const int workers = gpus * procs;   /* worker w runs on GPU w % gpus */
   int n = 0;
   struct family *fams = read_manifest(manifest, &n);
   /* longest-processing-time-first split over the workers */
@@ -348,26 +354,26 @@ main(int argc, char **argv)
     order[j + 1] = v;
   }
   int *owner = (int *) malloc((size_t) (n > 0 ? n : 1) * sizeof(int));
-  double *load = (double *) calloc((size_t) gpus, sizeof(double));
+  double *load = (double *) calloc((size_t) workers, sizeof(double));
   for (int k = 0; k < n; ++k)
   {
     int best = 0;
-    for (int g = 1; g < gpus; ++g)
+    for (int g = 1; g < workers; ++g)
       if (load[g] < load[best])
         best = g;
     owner[order[k]] = best;
     load[best] += fams[order[k]].cost;
   }
   int status = 0;
-  for (int g = 0; g < gpus; ++g)
+  for (int g = 0; g < workers; ++g)
   {
-    pid_t pid = gpus > 1 ? fork() : 0;
+    pid_t pid = workers > 1 ? fork() : 0;
     if (pid == 0)
     {
       if (gpus > 1)
       {
         char dev[16];
-        snprintf(dev, sizeof(dev), "%d", g);
+        snprintf(dev, sizeof(dev), "%d", g % gpus);
         setenv("RAMCU_DEVICE", dev, 1);
       }
       int m = 0;
@@ -377,7 +383,7 @@ main(int argc, char **argv)
           mine[m++] = &fams[i];
       if (m > 0)
         process(mine, m, chunk);
-      if (gpus > 1)
+      if (workers > 1)
         _exit(0);
     }
     else if (pid < 0)
@@ -386,7 +392,7 @@ main(int argc, char **argv)
       return 1;
     }
   }
-  if (gpus > 1)
+  if (workers > 1)
   {
     int st;
     while (wait(&st) > 0)

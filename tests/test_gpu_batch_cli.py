@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "repeatafterme_b200", "bin", "RAMExtendBatch")
 
 
-@pytest.mark.parametrize("chunk,gpus", [(512, 1), (4, 1)])
-def test_manifest_of_cli_cases_and_ce10_families(tmp_path, chunk, gpus):
+@pytest.mark.parametrize("chunk,gpus,procs", [(512, 1, 1), (4, 1, 1), (512, 1, 3)])
+def test_manifest_of_cli_cases_and_ce10_families(tmp_path, chunk, gpus, procs):
     if not os.path.exists(EXE):
         pytest.skip("bin/RAMExtendBatch not built (needs the reference's host objects)")
     from tests import ce10_standin as cs
@@ -43,7 +43,8 @@ def test_manifest_of_cli_cases_and_ce10_families(tmp_path, chunk, gpus):
         checks.append((str(d), gio.load_cli_outputs(f"ce10_fam{fam}"), str(gdir)))
     manifest = tmp_path / "manifest.txt"
     manifest.write_text("# one RAMExtend argument list per line\n" + "\n".join(lines) + "\n")
-    r = subprocess.run([EXE, "-chunk", str(chunk), "-gpus", str(gpus), str(manifest)], capture_output=True, text=True)
+    r = subprocess.run([EXE, "-chunk", str(chunk), "-gpus", str(gpus), "-procs", str(procs), str(manifest)],
+                       capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "families in" in r.stderr
     for chk in checks:

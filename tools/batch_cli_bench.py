@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 from repeatafterme_b200 import synth
 
 
-def main(k=24, pool=200, ref_timeout=600):
+def main(k=24, pool=200, ref_timeout=600, procs=1):
     specs = synth.config5_specs()
     ids = np.random.default_rng(1).permutation(len(specs))[:pool].tolist()
     ids.sort(key=lambda i: specs[i]["n"] * (2 * specs[i]["params"]["bandwidth"] + 1) * specs[i]["flank"])
@@ -35,10 +35,12 @@ def main(k=24, pool=200, ref_timeout=600):
     open(man, "w").write("\n".join(lines) + "\n")
     out = {"families": k, "instances": int(sum(specs[i]["n"] for i in ids)), "cell_updates_estimate": cu_est}
     t0 = time.perf_counter()
-    r = subprocess.run([os.path.join(ROOT, "repeatafterme_b200", "bin", "RAMExtendBatch"), man], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(ROOT, "repeatafterme_b200", "bin", "RAMExtendBatch"), "-procs", str(procs), man],
+                       capture_output=True, text=True)
     out["batch_wall_s"] = round(time.perf_counter() - t0, 3)
     assert r.returncode == 0, r.stderr[-2000:]
-    out["batch_report"] = r.stderr.strip().splitlines()[-1]
+    out["procs"] = procs
+    out["batch_report"] = r.stderr.strip().splitlines()[-procs:]
     out["batch_families_per_s"] = round(k / out["batch_wall_s"], 2)
     if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "RAMExtend")) and ref_timeout > 0:
         cmdfile = os.path.join(tmp, "ref_cmds.txt")
