@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -550,13 +551,51 @@ extern "C" int ramcu_library_free(ramcu_ctx *c, ramcu_library *lib)
 // CTA with the diagnostic / per-row outputs compiled in (jobs with `extras`)
 static extend_fn fn_of(const KernelCfg *k, int np) { return np == 2 ? k->fnx : k->fn[np]; }
 static int maxt_of(const KernelCfg *k, int np) { return k->maxt[np == 2 ? 0 : np]; }
+// Occupancy and stack size of a kernel do not change: asked once per (kernel, CTA size), then remembered (a
+// 2 000-family round plans 4 000 jobs over a dozen candidate tilings each; every GPU of a box is the same model).
+static std::mutex g_plan_mutex;
 static int ctas_per_sm(const KernelCfg *k, int np, int threads)
 {
-  int nb = 0;
-  if (!fn_of(k, np) ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *) fn_of(k, np), threads, 0) != cudaSuccess)
+  const extend_fn fn = fn_of(k, np);
+  if (!fn)
     return 0;
+  static std::map<std::pair<const void *, int>, int> cache;
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  const auto key = std::make_pair((const void *) fn, threads);
+  const auto it = cache.find(key);
+  if (it != cache.end())
+    return it->second;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *) fn, threads, 0) != cudaSuccess)
+  {
+    (void) cudaGetLastError();
+    return 0;
+  }
+  cache[key] = nb;
   return nb;
+}
+// stack bytes (ptxas spills) and registers of a kernel; false if it cannot be loaded
+static bool kernel_stack_and_regs(extend_fn fn, int *stack_bytes, int *regs)
+{
+  static std::map<const void *, std::pair<int, int>> cache;
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  const auto it = cache.find((const void *) fn);
+  if (it == cache.end())
+  {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, (const void *) fn) != cudaSuccess)
+    {
+      (void) cudaGetLastError();
+      return false;
+    }
+    cache[(const void *) fn] = std::make_pair((int) fa.localSizeBytes, fa.numRegs);
+    *stack_bytes = (int) fa.localSizeBytes;
+    *regs = fa.numRegs;
+    return true;
+  }
+  *stack_bytes = it->second.first;
+  *regs = it->second.second;
+  return true;
 }
 
 static int batch_threads(const KernelCfg *k, int np) { return std::min(kBatchThreads, maxt_of(k, np)); }
@@ -657,11 +696,9 @@ static double solo_cost(const ramcu_ctx *c, const KernelCfg *k, int np, int n_ex
   double squeeze = (65536.0 / maxt_of(k, np)) < need ? 1.5 : 1.0;
   if (squeeze == 1.0)
   {
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, (const void *) fn_of(k, np)) == cudaSuccess)
-      squeeze = (int) fa.localSizeBytes > 2 * fa.numRegs ? 1.3 : (int) fa.localSizeBytes > fa.numRegs ? 1.1 : 1.0;   // stack bytes per register
-    else
-      (void) cudaGetLastError();
+    int stack = 0, regs = 1;
+    if (kernel_stack_and_regs(fn_of(k, np), &stack, &regs))
+      squeeze = stack > 2 * regs ? 1.3 : stack > regs ? 1.1 : 1.0;   // stack bytes per register
   }
   const double instr = passes * ((k->G == 1 ? k->C * 15.0 + 250.0 : k->C * 18.0 + 320.0)) * squeeze;
   const int warps_per_cta = p.threads / 32;
