@@ -11,6 +11,6 @@ python bench.py --steps 3 --warmup 3 --families 96 > $O/bench_short.json 2> $O/b
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches.csv \
       python bench.py --steps 3 --warmup 3 --families 96 > $O/ncu_bench.log 2>&1
 echo "launch list rc=$?"
-CLI_BENCH_REFERENCE=1 timeout 300 python tools/cli_bench.py > $O/cli_bench.json 2> $O/cli_bench.err; echo "cli rc=$?"; cat $O/cli_bench.json
+timeout 300 python tools/cli_bench.py > $O/cli_bench.json 2> $O/cli_bench.err; echo "cli rc=$?"; cat $O/cli_bench.json
 timeout 400 python tools/batch_cli_bench.py 24 200 300 > $O/batch_cli.json 2> $O/batch_cli.err; echo "batchcli rc=$?"; cat $O/batch_cli.json
 ls -la $O
