@@ -324,8 +324,8 @@ def emul_extend_verbose(emul, cfg, direction, cores, seq, sc, p, n_rows, cells=F
                                       cand.ctypes.data, sums.ctypes.data, cel.ctypes.data if cells else None)
     assert rc == 0, f"emul_extend_verbose rc={rc}"
     rp = res.rows_processed
-    return dict(rows_processed=rp, extended_bp=res.extended_bp, master=master[:rp].copy(), cand=cand[:rp],
-                sums=sums[:rp], cells=(cel[:rp] if cells else None))
+    return dict(rows_processed=rp, extended_bp=res.extended_bp, master=master[:rp].copy(), ext_len=ext_len,
+                score_add=score_add, cand=cand[:rp], sums=sums[:rp], cells=(cel[:rp] if cells else None))
 
 
 def parse_verbose_dump(text):
