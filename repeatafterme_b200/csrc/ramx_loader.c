@@ -544,9 +544,23 @@ loadSequenceSubsetMinimal(char *twoBitName, char *rangeBEDName, struct coreAlign
     const uint64_t len = (uint64_t) (s->win_end - s->win_start);
     decode_window(&tb, rec, s->win_start, s->win_end, sequence + pos);
     /* N blocks overwrite (kentsrc/twoBitNew.c:597-613); everything that is not ACGT is 99 */
-    for (uint32_t b = 0; b < rec->n_blocks; ++b)
+    /* the blocks of a record are sorted and disjoint (the reference relies on it too:
+     * findGreatestLowerBound, kentsrc/twoBitNew.c:597): start at the last block that begins at or
+     * before the window, stop at the first one that begins behind it */
+    uint32_t b_lo = 0, b_hi = rec->n_blocks;
+    while (b_lo < b_hi)
+    {
+      const uint32_t mid = b_lo + (b_hi - b_lo) / 2;
+      if ((long) rd32(&tb, rec->nstart_off + 4ull * mid) <= s->win_start)
+        b_lo = mid + 1;
+      else
+        b_hi = mid;
+    }
+    for (uint32_t b = b_lo > 0 ? b_lo - 1 : 0; b < rec->n_blocks; ++b)
     {
       const long ns = (long) rd32(&tb, rec->nstart_off + 4ull * b);
+      if (ns >= s->win_end)
+        break;
       const long ne = ns + (long) rd32(&tb, rec->nsize_off + 4ull * b);
       const long a = ns > s->win_start ? ns : s->win_start, e = ne < s->win_end ? ne : s->win_end;
       if (a < e)

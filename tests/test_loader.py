@@ -78,6 +78,13 @@ def _inputs(name):
     if name == "n_runs":
         f = synth.make_family(61, 25, 300, 0.1, pad=40, one_sided_frac=0.3, n_frac=0.05)
         return f.names, f.seqs, f.bed, 250
+    if name == "many_n_blocks":    # dozens of N blocks per record, several windows on each record: the block search
+        n, s, b = cases.tandem_inputs(seed=9)
+        rng = np.random.default_rng(9)
+        for q in s:
+            for st in rng.integers(0, q.size - 12, 60).tolist():
+                q[st: st + int(rng.integers(1, 12))] = 99
+        return n, s, b, 150
     if name == "unsorted_duplicates":
         f = synth.make_family(62, 12, 120, 0.1, pad=10, one_sided_frac=0.3)
         bed = list(f.bed)[::-1] + [f.bed[3], f.bed[3][:3] + (0, 1, "-")]
@@ -100,7 +107,7 @@ def test_product_loader_equals_reference_loader_ce10_standin(ref):
             assert np.array_equal(_decode_windows(got, want_seq.size), want_seq)
 
 
-@pytest.mark.parametrize("name", ["satellite", "tandem", "overlap", "short_flank", "n_runs",
+@pytest.mark.parametrize("name", ["satellite", "tandem", "overlap", "short_flank", "n_runs", "many_n_blocks",
                                   "unsorted_duplicates"])
 def test_product_loader_equals_reference_loader(ref, name):
     names, seqs, bed, max_flank = _inputs(name)
