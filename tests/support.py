@@ -207,7 +207,7 @@ class Emulator:
                os.path.join(ROOT, "repeatafterme_b200", "csrc", "flatten.h")]
         path = os.path.join(EMUL_DIR, "libramemul.so")
         if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in src):
-            subprocess.check_call(["g++", "-std=c++17", "-O1", "-DRAMCU_EMUL", "-I.", "-fPIC", "-shared",
+            subprocess.check_call(["g++", "-std=c++17", "-O1", "-DRAMCU_EMUL", "-DRAMCU_CHECK", "-I.", "-fPIC", "-shared",
                                    "-pthread", "-o", "libramemul.so", "emul_driver.cpp"], cwd=EMUL_DIR)
         self.lib = lib = C.CDLL(path)
         lib.emul_extend.argtypes = [i32, i32, i32, i32, vp, u64, i32, i32, vp, P(Scoring), P(Params),
