@@ -5,8 +5,8 @@ Compiles every kernel translation unit of csrc/ with `-Xptxas -v` (objects go to
 product objects are left alone), disassembles them with `cuobjdump -sass` and writes
 profiles/r2_ptxas_sass.md:
   * registers / spill bytes / shared memory of every extend_kernel instantiation (ptxas -v),
-  * the opcode histogram of the instantiations named on the command line (default: the config-4 tiling and the
-    tilings of the genome-scale mix), whole kernel and the hottest loop bodies are not separated: the histogram is static.
+  * the opcode histogram of the instantiations named on the command line (default: the config-4 tiling, a two-pass tiling and the
+    fewest-lane tilings a crowded genome-scale batch runs), whole kernel and the hottest loop bodies are not separated: the histogram is static.
 """
 from __future__ import annotations
 
@@ -23,8 +23,8 @@ CSRC = os.path.join(ROOT, "repeatafterme_b200", "csrc")
 sys.path.insert(0, ROOT)
 from repeatafterme_b200.build import ARCH, KERNEL_UNITS, NVCC  # noqa: E402
 
-HIST = ["27, 3, 81, 256, 2", "27, 3, 81, 384, 1", "21, 2, 41, 256, 2", "31, 4, 121, 256, 2", "33, 5, 161, 256, 2",
-        "34, 6, 201, 256, 2"]
+HIST = ["81, 1, 81, 256, 1, false", "27, 3, 81, 256, 2, false", "29, 1, 29, 384, 1, false", "41, 1, 41, 384, 1, false",
+        "41, 3, 121, 384, 1, false", "41, 4, 161, 384, 1, false", "41, 5, 201, 384, 1, false"]
 
 
 def compile_unit(unit, tmp):
