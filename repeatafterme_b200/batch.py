@@ -54,11 +54,14 @@ def _as_dict(res, master, ext_len, score_add, bandwidth):
     return d
 
 
-def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
+def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True, timing=None):
     """Extend a list of families (objects with .sequence or .blob, .cores, .params: synth.Family or
     synth.PackedFamily).
     Host buffers in, host results out: library upload, every pass of every family as one batch
-    (or right batch, `between_passes` hook, left batch), fetch."""
+    (or right batch, `between_passes` hook, left batch), fetch.
+    timing: a dict that receives the host wall clock of the phases (seconds): upload, create, run_fetch."""
+    import time
+    t_begin = time.perf_counter()
     libs, scs, prs = [], [], []
     total = sum(int(f.cores.size) for f in fams)
     for f in fams:
@@ -75,6 +78,8 @@ def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
         else:
             libs.append(rc.upload_library(f.sequence))
     results = [FamilyResult() for _ in fams]
+    t_upload = time.perf_counter()
+    t_create = t_upload
     try:
         # Without a between-passes step (the overlap avoidance of ram_extend.c:445-499 belongs to the
         # caller) the left passes do not depend on the right ones: all 2 x len(fams) column loops go
@@ -87,6 +92,7 @@ def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
                 r, l = rc.job_create_pair(libs[i], f.cores, scs[i], prs[i])
                 jobs += [(i, 1, r), (i, 0, l)]
             rounds = [jobs]
+            t_create = time.perf_counter()
         else:
             rounds = [(1,), (0,)]
         for rnd in rounds:
@@ -109,4 +115,9 @@ def extend_families(rc: RamCu, fams, between_passes=None, concurrent_hint=True):
     finally:
         for h in libs:
             rc.free_library(h)
+    if timing is not None:
+        t_end = time.perf_counter()
+        timing["upload"] = timing.get("upload", 0.0) + (t_upload - t_begin)
+        timing["create"] = timing.get("create", 0.0) + (t_create - t_upload)
+        timing["run_fetch"] = timing.get("run_fetch", 0.0) + (t_end - t_create)
     return results
