@@ -26,6 +26,7 @@ using std::min;
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
 struct uint2 { unsigned x, y; };
+struct int2 { int x, y; };
 struct dim3e { unsigned x, y, z; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 v = {x, y, z, w}; return v; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 v = {x, y}; return v; }
@@ -124,6 +125,13 @@ static inline unsigned __brev(unsigned x)
   x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
   x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
   return __builtin_bswap32(x);
+}
+// c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (signed)
+static inline int __dp2a_lo(int a, int b, int c)
+{
+  const int lo = (int) (short) (a & 0xffff), hi = (int) (short) ((unsigned) a >> 16);
+  const int b0 = (int) (signed char) (b & 0xff), b1 = (int) (signed char) ((b >> 8) & 0xff);
+  return (int) ((unsigned) c + (unsigned) (lo * b0) + (unsigned) (hi * b1));
 }
 static inline void __threadfence_block() { __sync_synchronize(); }
 static inline void __syncwarp()

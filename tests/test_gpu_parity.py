@@ -97,6 +97,39 @@ def test_random_families_vs_oracle(ramcu, oracle, seed, n, flank, B, matrix, kw)
         ramcu.free_library(lib)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale,B,n", [(3000, 14, 60), (1500, 14, 60), (2000, 40, 300), (700, 40, 300)])
+def test_scores_beyond_int16_vs_oracle(ramcu, oracle, scale, B, n):
+    """the sweep reads the candidate scores as int16 (IDP.2A); a matrix beyond that range must take the exact
+    path (the ABI accepts |score| * (L + 2B + 3) <= 1.2e7): scaled 14p43g on both sides of the int16 limit,
+    every tiling of the band"""
+    fam = synth.make_family(93 + n, n, 120, 0.15, pad=40, one_sided_frac=0.2, n_frac=0.01)
+    osc = oracle.scoring("14p43g")
+    for a in range(4):
+        for b in range(9):
+            osc.matrix[a][b] *= scale
+    osc.gapopen *= scale
+    osc.gapextn *= scale
+    L = 60 if B == 14 else 30   # |gapopen| + |gapext| = 40 * scale: inside the accepted range
+    lib = ramcu.upload_library(fam.sequence)
+    ran = 0
+    try:
+        for G in (0, 1, 2, 3, 4, 8):
+            p = make_params(bandwidth=B, minimprovement=27 * scale, L=L, when_to_stop=30, lanes_per_instance=G)
+            for d in (1, 0):
+                want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+                try:
+                    got = _got(*ramcu.extend(lib, d, fam.cores, osc.to_product(), p))
+                except RamCuError as ex:
+                    assert "no band tiling" in str(ex), ex
+                    continue
+                support.compare_extend(want, got, f"scale={scale} B={B} G={G} dir={d}")
+                ran += 1
+    finally:
+        ramcu.free_library(lib)
+    assert ran >= 4
+
+
 def test_rows_and_sums_vs_oracle_trace(ramcu, oracle):
     """per-row column sums / chosen base (the argmax) and per-candidate bests vs the oracle"""
     fam = synth.make_family(7, 40, 150, 0.15, one_sided_frac=0.2)

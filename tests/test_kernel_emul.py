@@ -174,6 +174,28 @@ def test_emul_positive_gap_penalties(emul, oracle, cfg, gaps):
         support.compare_extend(want, got, f"cfg={cfg} gaps={gaps} dir={d}")
 
 
+@pytest.mark.parametrize("cfg,scale", [((29, 1, 29), 3000), ((10, 3, 29), 3000), ((15, 2, 29), 1500)])
+def test_emul_scores_beyond_int16(emul, oracle, cfg, scale):
+    """the sweep reads the candidate scores as int16 (IDP.2A); a matrix beyond that range (the ABI accepts
+    |score| * (L + 2B + 3) <= 1.2e7) must take the exact path: scaled 14p43g with entries of several 10 000,
+    and a scale whose entries still fit (the packed path with large scores)"""
+    fam = synth.make_family(93, 11, 120, 0.15, pad=40, one_sided_frac=0.2, n_frac=0.01)
+    osc = oracle.scoring("14p43g")
+    for a in range(4):
+        for b in range(9):
+            osc.matrix[a][b] *= scale
+    osc.gapopen *= scale
+    osc.gapextn *= scale
+    big = max(abs(int(osc.matrix[a][b])) for a in range(4) for b in range(9))
+    assert (big > 32767) == (scale == 3000)
+    p = make_params(bandwidth=14, minimprovement=27 * scale, L=80, when_to_stop=30)
+    for d in (1, 0):
+        want = oracle.extend(d, fam.cores, fam.sequence, osc, p)
+        assert want["rows_processed"] > 40
+        got = emul.extend(cfg, d, fam.cores, fam.sequence, osc.to_product(), p, threads=64)
+        support.compare_extend(want, got, f"cfg={cfg} scale={scale} dir={d}")
+
+
 @pytest.mark.parametrize("cfg,B,threads,n", [((10, 3, 29), 14, 64, 23), ((8, 4, 29), 14, 32, 9), ((29, 1, 29), 14, 64, 70),
                                            ((27, 3, 81), 40, 32, 12), ((16, 4, 0), 20, 64, 17)])
 def test_emul_two_passes_in_the_same_threads(emul, oracle, cfg, B, threads, n):
