@@ -4,7 +4,9 @@ import subprocess
 import sys
 
 rep, out, title = sys.argv[1], sys.argv[2], sys.argv[3]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# a .csv argument is the output of `ncu -i X.ncu-rep --page raw --csv` made on the GPU box
+raw = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 lines = raw.splitlines()
 start = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
 rows = list(csv.reader(lines[start:]))
