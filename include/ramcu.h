@@ -70,7 +70,10 @@ typedef struct
 } ramcu_core_t;
 
 /* matrix[consensus base 0..3][sequence code]: codes 0..3 = A,C,G,T, 4 = N (SYM_N and anything
- * that is not 0..3). */
+ * that is not 0..3). Accepted range: (max |entry|, |gapopen| + |gapextn|) x (L + 2 * bandwidth + 3) <= 12 000 000
+ * (job creation refuses more: the reference's -1000000000 floor could be crossed). Results are exact for every
+ * accepted value; matrices whose entries all fit int16 -- every matrix of score_system.c -- run the fast rows,
+ * others the exact per-cell path on every row (same results, several times slower). */
 typedef struct
 {
   int32_t matrix[4][RAMCU_NCODES];
