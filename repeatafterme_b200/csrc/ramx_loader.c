@@ -91,9 +91,11 @@ read_ranges(const char *path, int *n_out)
   FILE *fh = fopen(path, "rb");
   if (!fh)
     die("Couldn't open %s , %s", path, strerror(errno));
-  fseek(fh, 0, SEEK_END);
-  long size = ftell(fh);
-  fseek(fh, 0, SEEK_SET);
+  long size = -1;
+  if (fseek(fh, 0, SEEK_END) == 0)
+    size = ftell(fh);
+  if (size < 0 || fseek(fh, 0, SEEK_SET) != 0)
+    die("Couldn't read %s: %s", path, "not a regular file");
   char *buf = (char *) malloc((size_t) size + 2);
   if (!buf || fread(buf, 1, (size_t) size, fh) != (size_t) size)
     die("Couldn't read %s%s", path, "");
@@ -102,6 +104,8 @@ read_ranges(const char *path, int *n_out)
   buf[size + 1] = 0;
   int cap = 1024, n = 0;
   struct range *r = (struct range *) malloc(cap * sizeof(*r));
+  if (!r)
+    die("Out of memory reading %s%s", path, "");
   char *line = buf, *end = buf + size;
   while (line < end)
   {
@@ -133,6 +137,8 @@ read_ranges(const char *path, int *n_out)
       {
         cap *= 2;
         r = (struct range *) realloc(r, cap * sizeof(*r));
+        if (!r)
+          die("Out of memory reading %s%s", path, "");
       }
       char *e;
       memset(&r[n], 0, sizeof(r[n]));
@@ -251,7 +257,11 @@ twobit_open(struct twobit *t, const char *path)
   if (t->version != 0 && t->version != 1)
     die("Can only handle version 0 or version 1 of this file. This is version %s%s", "?", "");
   t->n_records = (int) rd32(t, 8);
+  if (t->n_records < 0)
+    die("%s: corrupt sequence count%s", path, "");
   t->rec = (struct record *) calloc((size_t) (t->n_records > 0 ? t->n_records : 1), sizeof(struct record));
+  if (!t->rec)
+    die("%s: out of memory for the index%s", path, "");
   uint64_t p = 16;
   for (int i = 0; i < t->n_records; ++i)
   {
@@ -366,6 +376,8 @@ nrange_push(uint64_t start, uint64_t len)
     g_source.cap_nranges = g_source.cap_nranges ? 2 * g_source.cap_nranges : 256;
     g_source.n_start = (uint64_t *) realloc(g_source.n_start, (size_t) g_source.cap_nranges * sizeof(uint64_t));
     g_source.n_len = (uint64_t *) realloc(g_source.n_len, (size_t) g_source.cap_nranges * sizeof(uint64_t));
+    if (!g_source.n_start || !g_source.n_len)
+      die("%s: out of memory for the N runs%s", "loadSequenceSubsetMinimal", "");
   }
   g_source.n_start[g_source.n_nranges] = start;
   g_source.n_len[g_source.n_nranges] = len;
